@@ -1,0 +1,139 @@
+/*
+ * sccoda_b200 — C ABI of the B200-native MCMC engine for scCODA's Dirichlet-multinomial model.
+ *
+ * This is the drop-in boundary for the reference's sampler path.  Each entry point names the reference
+ * interface it replaces (paths relative to the upstream repository theislab/scCODA):
+ *
+ *   sccoda_logp_grad      scCODAModel.target_log_prob_fn + TF autodiff      sccoda/model/scCODA_model.py:756-760
+ *   sccoda_sample         CompositionalModel.sampling -> tfp.mcmc.sample_chain
+ *                         with the kernel stacks of sample_hmc / sample_hmc_da / sample_nuts
+ *                                                                            sccoda/model/scCODA_model.py:152-161,
+ *                                                                            :276-315, :382-424, :495-553
+ *   sccoda_summarize      the per-draw post-processing of get_y_hat and CAResult.complete_beta_df
+ *                                                                            sccoda/model/scCODA_model.py:800-834,
+ *                                                                            sccoda/util/result_classes.py:240-258
+ *   sccoda_sample_host    the same sampling call with HOST buffers (what a Python/ctypes caller that owns
+ *                         numpy arrays binds; copies host<->device inside)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no framework types.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = default stream).  All *device* entry points are asynchronous on `stream` and never
+ *     synchronise the host.
+ *   - every real-valued array has element type float (dtype == SCCODA_F32) or double (SCCODA_F64).
+ *   - return value: 0 on success, negative error code otherwise; sccoda_last_error() gives the text.
+ *   - thread-compatible, not thread-safe: one host thread per device context.
+ *
+ * Packed dataset layout (built by sccoda_b200/_pack.py or by the caller; B datasets of equal shape):
+ *   y       [B,N,K]     counts after the 0.5 pseudocount (scCODA_model.py:94-96), rows sorted by covariate group
+ *   ycst    [B,N,K]     per-count constant: fp32 -> r(y) if y>=6 else lgamma(y); fp64 -> 0   (see csrc/special.cuh)
+ *   ntot    [B,N]       row sums of y (scCODA_model.py:99-100)
+ *   xu      [B,Umax,D]  unique covariate rows (design matrix without intercept, comp_ana.py:73-75)
+ *   grp     [B,N] i32   covariate group of each row, non-decreasing
+ *   rstart  [B,Umax+1] i32  first row of each group (rstart[U..] = N)
+ *   U       [B] i32     number of groups of dataset b (<= Umax)
+ *   ref     [B] i32     reference cell type (scCODA_model.py:688)
+ *   lconst  [B] f64     all parameter-independent terms of the log-density
+ *
+ * State vector (P = D + 2 D (K-1) + K), order of scCODA_model.py:692-693:
+ *   [ sigma_d (D) | b_offset (D,K-1) | ind_raw (D,K-1) | alpha (K) ]
+ */
+#ifndef SCCODA_B200_H
+#define SCCODA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCCODA_F32 0
+#define SCCODA_F64 1
+
+#define SCCODA_METHOD_HMC 0    /* HMC + SimpleStepSizeAdaptation          (sample_hmc,    :276-289) */
+#define SCCODA_METHOD_HMC_DA 1 /* HMC + DualAveragingStepSizeAdaptation   (sample_hmc_da, :382-395) */
+#define SCCODA_METHOD_NUTS 2   /* NUTS + DualAveragingStepSizeAdaptation  (sample_nuts,   :495-519) */
+
+/* per-draw statistics, stats[B,C,S,SCCODA_NSTAT] (trace_fn of :296-311, :402-420, :526-550) */
+#define SCCODA_NSTAT 8
+#define SCCODA_ST_TARGET_LOG_PROB 0
+#define SCCODA_ST_LOG_ACCEPT_RATIO 1
+#define SCCODA_ST_IS_ACCEPTED 2
+#define SCCODA_ST_STEP_SIZE 3
+#define SCCODA_ST_DIVERGING 4
+#define SCCODA_ST_LEAPFROGS_TAKEN 5
+#define SCCODA_ST_ENERGY 6
+#define SCCODA_ST_REACH_MAX_DEPTH 7
+
+/* carry[B,C,P+SCCODA_NCARRY] f64: chain state for chunked launches (resume points) */
+#define SCCODA_NCARRY 8
+
+/* summary[B,C,SCCODA_NSUM_PARAM*P + SCCODA_NSUM_BETA*D*K + SCCODA_NSUM_SCALAR] f64 — see sccoda_summarize */
+#define SCCODA_NSUM_PARAM 2  /* mean, M2 (sum of squared deviations) of every state coordinate */
+#define SCCODA_NSUM_BETA 4   /* per (d,k): inclusion count (|beta|>1e-3), sum of included beta, mean, M2 of beta */
+#define SCCODA_NSUM_SCALAR 6 /* over ALL traced steps (scCODA_model.py:218-224): draws used after skip, accepted
+                                steps, sum exp(min(log_accept_ratio,0)), leapfrogs, diverging steps, last step size */
+
+typedef struct sccoda_problem {
+    int32_t B, C;          /* datasets, chains per dataset */
+    int32_t N, K, D, Umax; /* samples, cell types, covariates, max covariate groups */
+    int32_t dtype;         /* SCCODA_F32 / SCCODA_F64 */
+    int32_t reserved;
+    const void* y;
+    const void* ycst;
+    const void* ntot;
+    const void* xu;
+    const int32_t* grp;
+    const int32_t* rstart;
+    const int32_t* U;
+    const int32_t* ref;
+    const double* lconst;
+} sccoda_problem;
+
+typedef struct sccoda_sampler {
+    int32_t method;         /* SCCODA_METHOD_* */
+    int32_t num_results;    /* traced draws S  (reference default 20000 / 10000) */
+    int32_t num_burnin;     /* untraced leading steps (reference default 5000)   */
+    int32_t num_adapt;      /* adaptation steps (reference: int(0.8*num_burnin)) */
+    int32_t num_leapfrog;   /* HMC leapfrog steps (reference default 10)         */
+    int32_t max_tree_depth; /* NUTS (reference default 10)                       */
+    int32_t step_begin;     /* chunking: run steps [step_begin, step_end) of num_burnin+num_results */
+    int32_t step_end;       /* 0 => run to the end */
+    double step_size;       /* initial step size (reference default 0.01) */
+    double target_accept;   /* reference: 0.75 */
+    uint64_t seed;
+    uint32_t chain_id0;     /* global id of chain (b=0,c=0): lets shards on different GPUs keep disjoint streams */
+    int32_t warps_per_chain; /* 0 = choose automatically; 1,2,4,8,16 */
+    int32_t store_draws;    /* 1 = write draws/stats (default); 0 = only carry (e.g. warm-up chunks) */
+    int32_t reserved;
+} sccoda_sampler;
+
+/* Library / device info. */
+int sccoda_version(void);
+const char* sccoda_last_error(void);
+
+/* Value and gradient of the log-density at theta[B,C,P] -> logp[B,C] (f64), grad[B,C,P] (dtype). */
+int sccoda_logp_grad(const sccoda_problem* prob, const void* theta, double* logp, void* grad, void* stream);
+
+/* Run the sampler.  init[B,C,P]; draws[B,C,S,P]; stats[B,C,S,SCCODA_NSTAT]; carry[B,C,P+SCCODA_NCARRY] f64
+ * (may be NULL when step_begin==0 and the run is not chunked). All device pointers. */
+int sccoda_sample(const sccoda_problem* prob, const sccoda_sampler* smp, const void* init, void* draws, void* stats,
+                  double* carry, void* stream);
+
+/* Per-chain posterior summaries straight from device-resident draws (skip = python-side second burn-in,
+ * scCODA_model.py:205-227).  summary[B,C,*] f64, layout above. */
+int sccoda_summarize(const sccoda_problem* prob, int32_t num_results, int32_t skip, const void* draws,
+                     const void* stats, double* summary, void* stream);
+
+/* Bytes of dynamic shared memory and threads per CTA the sampler would use (for planning / tests). */
+int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* warps_per_chain,
+                       int32_t* chains_per_cta, int32_t* grid, int32_t* smem_bytes);
+
+/* Host-buffer convenience (the end-to-end path): all pointers are HOST memory; copies in, runs on `device`,
+ * copies draws/stats (either may be NULL) and, if summary != NULL, the summaries back.  Synchronous. */
+int sccoda_sample_host(const sccoda_problem* prob_host, const sccoda_sampler* smp, const void* init, void* draws,
+                       void* stats, double* summary, int32_t summary_skip, int32_t device, float* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCCODA_B200_H */

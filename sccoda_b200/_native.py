@@ -1,0 +1,72 @@
+"""
+ctypes binding of the C ABI in include/sccoda_b200.h (libsccoda_b200.so, built in-tree by csrc/build.sh).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsccoda_b200.so")
+
+F32, F64 = 0, 1
+METHOD_HMC, METHOD_HMC_DA, METHOD_NUTS = 0, 1, 2
+NSTAT = 8
+STAT_NAMES = ("target_log_prob", "log_accept_ratio", "is_accepted", "step_size", "diverging",
+              "leapfrogs_taken", "energy", "reach_max_depth")
+NCARRY = 8
+NSUM_PARAM, NSUM_BETA, NSUM_SCALAR = 2, 4, 6
+
+EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sample", "sccoda_summarize",
+           "sccoda_launch_plan", "sccoda_sample_host")
+
+
+class Problem(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int32), ("C", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+                ("D", ctypes.c_int32), ("Umax", ctypes.c_int32), ("dtype", ctypes.c_int32),
+                ("reserved", ctypes.c_int32),
+                ("y", ctypes.c_void_p), ("ycst", ctypes.c_void_p), ("ntot", ctypes.c_void_p), ("xu", ctypes.c_void_p),
+                ("grp", ctypes.c_void_p), ("rstart", ctypes.c_void_p), ("U", ctypes.c_void_p),
+                ("ref", ctypes.c_void_p), ("lconst", ctypes.c_void_p)]
+
+
+class Sampler(ctypes.Structure):
+    _fields_ = [("method", ctypes.c_int32), ("num_results", ctypes.c_int32), ("num_burnin", ctypes.c_int32),
+                ("num_adapt", ctypes.c_int32), ("num_leapfrog", ctypes.c_int32), ("max_tree_depth", ctypes.c_int32),
+                ("step_begin", ctypes.c_int32), ("step_end", ctypes.c_int32),
+                ("step_size", ctypes.c_double), ("target_accept", ctypes.c_double),
+                ("seed", ctypes.c_uint64), ("chain_id0", ctypes.c_uint32), ("warps_per_chain", ctypes.c_int32),
+                ("store_draws", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libsccoda_b200.so; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"sccoda_b200: native library {LIB_PATH} is missing. Build it with "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` or sccoda_b200/csrc/build.sh. "
+                f"There is no CPU fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        vp, i32 = ctypes.c_void_p, ctypes.c_int32
+        pp, sp = ctypes.POINTER(Problem), ctypes.POINTER(Sampler)
+        _lib.sccoda_version.restype = ctypes.c_int
+        _lib.sccoda_last_error.restype = ctypes.c_char_p
+        _lib.sccoda_logp_grad.argtypes = [pp, vp, vp, vp, vp]
+        _lib.sccoda_sample.argtypes = [pp, sp, vp, vp, vp, vp, vp]
+        _lib.sccoda_summarize.argtypes = [pp, i32, i32, vp, vp, vp, vp]
+        _lib.sccoda_launch_plan.argtypes = [pp, sp] + [ctypes.POINTER(i32)] * 4
+        _lib.sccoda_sample_host.argtypes = [pp, sp, vp, vp, vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float)]
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().sccoda_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"sccoda_b200 native call {what} failed (code {rc}): {msg}")

@@ -1,0 +1,260 @@
+// C ABI (extern "C") of libsccoda_b200.so — see include/sccoda_b200.h.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/sccoda_b200.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) return fail(-100, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+uint32_t magic_for(int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d); }
+
+int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+int pow2_floor(int v) {
+    int p = 1;
+    while (p * 2 <= v) p <<= 1;
+    return p;
+}
+
+int validate(const sccoda_problem* p) {
+    if (!p) return fail(-1, "problem is NULL");
+    if (p->B < 1 || p->C < 1) return fail(-2, "need B >= 1 and C >= 1 (got B=%d C=%d)", p->B, p->C);
+    if (p->N < 1 || p->K < 2 || p->D < 1) return fail(-3, "need N >= 1, K >= 2, D >= 1 (got N=%d K=%d D=%d)", p->N, p->K, p->D);
+    if (p->Umax < 1 || p->Umax > p->N) return fail(-4, "need 1 <= Umax <= N (got Umax=%d N=%d)", p->Umax, p->N);
+    if (p->dtype != SCCODA_F32 && p->dtype != SCCODA_F64) return fail(-5, "dtype must be SCCODA_F32 or SCCODA_F64");
+    if ((uint64_t)p->N * p->K * p->K >= 0x100000000ull) return fail(-6, "N*K*K must be < 2^32");
+    if (!p->y || !p->ycst || !p->ntot || !p->xu || !p->grp || !p->rstart || !p->U || !p->ref || !p->lconst)
+        return fail(-7, "problem has a NULL array");
+    return 0;
+}
+
+void fill_dims(const sccoda_problem* p, sccoda::KArgs& a) {
+    a.dm.N = p->N; a.dm.K = p->K; a.dm.D = p->D;
+    a.dm.K1 = p->K - 1; a.dm.DK1 = p->D * (p->K - 1); a.dm.NK = p->N * p->K;
+    a.dm.P = p->D + 2 * a.dm.DK1 + p->K;
+    a.dm.magicK = magic_for(p->K);
+    a.dm.magicK1 = magic_for(p->K - 1);  // 0 encodes a divisor of 1 (K == 2)
+    a.B = p->B; a.C = p->C; a.Umax = p->Umax;
+    a.y = p->y; a.ycst = p->ycst; a.ntot = p->ntot; a.xu = p->xu;
+    a.grp = p->grp; a.rstart = p->rstart; a.U = p->U; a.ref = p->ref; a.lconst = p->lconst;
+}
+
+struct Plan {
+    int W, cpc, grid, smem;
+};
+
+int make_plan(const sccoda_problem* p, const sccoda::KArgs& a, int kind, int W_req, Plan* out) {
+    int dev = 0, max_smem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+        cudaGetLastError();
+        max_smem = 227 * 1024;  // B200; used only for planning without a device
+    }
+    const int NK = p->N * p->K;
+    int W = W_req;
+    if (W == 0) {
+        const int n_chains = p->B * p->C;
+        const int w_work = pow2_ceil((NK + 511) / 512);
+        const int fill = (148 * 8) / n_chains;  // warps per chain that would give ~8 warps per SM
+        const int w_fill = pow2_floor(fill > 0 ? fill : 1);
+        const int w_cap = pow2_ceil((NK + 31) / 32);  // never fewer than one element per thread
+        const int w_lim = w_fill < w_cap ? w_fill : w_cap;
+        W = w_work > w_lim ? w_work : w_lim;
+        if (W > 16) W = 16;
+        if (W < 1) W = 1;
+    }
+    if (W != 1 && W != 2 && W != 4 && W != 8 && W != 16) return fail(-8, "warps_per_chain must be 0,1,2,4,8,16");
+    int cpc = 128 / (32 * W);
+    if (cpc < 1) cpc = 1;
+    if (cpc > p->C) cpc = p->C;
+    while (cpc > 1 && (int)sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype) > max_smem) cpc -= 1;
+    const size_t smem = sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype);
+    if ((int)smem > max_smem)
+        return fail(-9, "problem needs %zu bytes of shared memory per chain group, device limit is %d", smem, max_smem);
+    out->W = W; out->cpc = cpc; out->smem = (int)smem;
+    out->grid = p->B * ((p->C + cpc - 1) / cpc);
+    return 0;
+}
+
+int fill_sampler(const sccoda_sampler* s, sccoda::KArgs& a, int* kind) {
+    if (!s) return fail(-10, "sampler is NULL");
+    if (s->method < 0 || s->method > 2) return fail(-11, "unknown method %d", s->method);
+    if (s->num_results < 1 || s->num_burnin < 0) return fail(-12, "need num_results >= 1 and num_burnin >= 0");
+    if (s->method != SCCODA_METHOD_NUTS && s->num_leapfrog < 1) return fail(-13, "need num_leapfrog >= 1");
+    if (s->method == SCCODA_METHOD_NUTS && (s->max_tree_depth < 1 || s->max_tree_depth > 20))
+        return fail(-14, "need 1 <= max_tree_depth <= 20");
+    if (!(s->step_size > 0.0)) return fail(-15, "need step_size > 0");
+    a.method = s->method; a.num_results = s->num_results; a.num_burnin = s->num_burnin; a.num_adapt = s->num_adapt;
+    a.num_leapfrog = s->num_leapfrog; a.max_depth = s->method == SCCODA_METHOD_NUTS ? s->max_tree_depth : 0;
+    a.step_begin = s->step_begin;
+    a.step_end = s->step_end > 0 ? s->step_end : s->num_burnin + s->num_results;
+    if (a.step_begin < 0 || a.step_end > s->num_burnin + s->num_results || a.step_begin > a.step_end)
+        return fail(-16, "bad step range [%d,%d)", a.step_begin, a.step_end);
+    a.store_draws = s->store_draws;
+    a.step_size = s->step_size; a.target_accept = s->target_accept; a.seed = s->seed; a.chain_id0 = s->chain_id0;
+    *kind = s->method == SCCODA_METHOD_NUTS ? sccoda::KIND_NUTS : sccoda::KIND_HMC;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sccoda_version(void) { return 100; }
+
+const char* sccoda_last_error(void) { return g_err; }
+
+int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* warps_per_chain,
+                       int32_t* chains_per_cta, int32_t* grid, int32_t* smem_bytes) {
+    int rc = validate(prob);
+    if (rc) return rc;
+    sccoda::KArgs a{};
+    fill_dims(prob, a);
+    int kind = 0;
+    rc = fill_sampler(smp, a, &kind);
+    if (rc) return rc;
+    Plan pl;
+    rc = make_plan(prob, a, kind, smp->warps_per_chain, &pl);
+    if (rc) return rc;
+    if (warps_per_chain) *warps_per_chain = pl.W;
+    if (chains_per_cta) *chains_per_cta = pl.cpc;
+    if (grid) *grid = pl.grid;
+    if (smem_bytes) *smem_bytes = pl.smem;
+    return 0;
+}
+
+int sccoda_logp_grad(const sccoda_problem* prob, const void* theta, double* logp, void* grad, void* stream) {
+    int rc = validate(prob);
+    if (rc) return rc;
+    if (!theta || !logp || !grad) return fail(-20, "theta/logp/grad must not be NULL");
+    sccoda::KArgs a{};
+    fill_dims(prob, a);
+    a.init = theta; a.draws = grad; a.carry = logp;
+    Plan pl;
+    rc = make_plan(prob, a, sccoda::KIND_LOGP, 0, &pl);
+    if (rc) return rc;
+    CUDA_TRY(sccoda::launch_kernel(sccoda::KIND_LOGP, prob->dtype, pl.W, pl.cpc, a, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int sccoda_sample(const sccoda_problem* prob, const sccoda_sampler* smp, const void* init, void* draws, void* stats,
+                  double* carry, void* stream) {
+    int rc = validate(prob);
+    if (rc) return rc;
+    sccoda::KArgs a{};
+    fill_dims(prob, a);
+    int kind = 0;
+    rc = fill_sampler(smp, a, &kind);
+    if (rc) return rc;
+    if (a.step_begin == 0 && !init) return fail(-21, "init must not be NULL when step_begin == 0");
+    if (a.step_begin > 0 && !carry) return fail(-22, "carry must not be NULL when resuming (step_begin > 0)");
+    if (a.store_draws && (!draws || !stats)) return fail(-23, "draws/stats must not be NULL when store_draws != 0");
+    a.init = init; a.draws = draws; a.stats = stats; a.carry = carry;
+    Plan pl;
+    rc = make_plan(prob, a, kind, smp->warps_per_chain, &pl);
+    if (rc) return rc;
+    CUDA_TRY(sccoda::launch_kernel(kind, prob->dtype, pl.W, pl.cpc, a, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int sccoda_summarize(const sccoda_problem* prob, int32_t num_results, int32_t skip, const void* draws,
+                     const void* stats, double* summary, void* stream) {
+    int rc = validate(prob);
+    if (rc) return rc;
+    if (!draws || !stats || !summary) return fail(-30, "draws/stats/summary must not be NULL");
+    if (skip < 0 || skip > num_results) return fail(-31, "need 0 <= skip <= num_results");
+    CUDA_TRY(sccoda::launch_summary(prob->dtype, prob->B, prob->C, prob->N, prob->K, prob->D, prob->ref, num_results, skip,
+                                    draws, stats, summary, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, const void* init, void* draws, void* stats,
+                       double* summary, int32_t summary_skip, int32_t device, float* kernel_ms) {
+    if (!ph || !smp) return fail(-40, "NULL argument");
+    if (ph->B < 1 || ph->C < 1 || ph->N < 1 || ph->K < 2 || ph->D < 1 || ph->Umax < 1) return fail(-41, "bad problem dimensions");
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t ts = ph->dtype == SCCODA_F64 ? 8 : 4;
+    const size_t B = ph->B, C = ph->C, N = ph->N, K = ph->K, D = ph->D, U = ph->Umax, S = smp->num_results;
+    const size_t P = D + 2 * D * (K - 1) + K;
+    struct Buf { void** dp; const void* hp; size_t bytes; };
+    sccoda_problem pd = *ph;
+    void *d_y = nullptr, *d_ycst = nullptr, *d_ntot = nullptr, *d_xu = nullptr, *d_grp = nullptr, *d_rstart = nullptr,
+         *d_U = nullptr, *d_ref = nullptr, *d_lconst = nullptr, *d_init = nullptr, *d_draws = nullptr, *d_stats = nullptr,
+         *d_sum = nullptr;
+    Buf in[] = {{&d_y, ph->y, B * N * K * ts}, {&d_ycst, ph->ycst, B * N * K * ts}, {&d_ntot, ph->ntot, B * N * ts},
+                {&d_xu, ph->xu, B * U * D * ts}, {&d_grp, ph->grp, B * N * 4}, {&d_rstart, ph->rstart, B * (U + 1) * 4},
+                {&d_U, ph->U, B * 4}, {&d_ref, ph->ref, B * 4}, {&d_lconst, ph->lconst, B * 8},
+                {&d_init, init, B * C * P * ts}};
+    std::vector<void*> to_free;
+    auto cleanup = [&]() { for (void* p : to_free) cudaFree(p); };
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreate(&st));
+    int rc = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        for (auto& b : in) {
+            if (cudaMalloc(b.dp, b.bytes) != cudaSuccess) { rc = fail(-42, "cudaMalloc(%zu) failed", b.bytes); break; }
+            to_free.push_back(*b.dp);
+            if (cudaMemcpyAsync(*b.dp, b.hp, b.bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail(-43, "H2D copy failed"); break; }
+        }
+        if (rc) break;
+        const size_t draws_bytes = B * C * S * P * ts, stats_bytes = B * C * S * SCCODA_NSTAT * ts;
+        const size_t nsum = SCCODA_NSUM_PARAM * P + SCCODA_NSUM_BETA * D * K + SCCODA_NSUM_SCALAR;
+        if (cudaMalloc(&d_draws, draws_bytes) != cudaSuccess) { rc = fail(-42, "cudaMalloc(draws, %zu) failed", draws_bytes); break; }
+        to_free.push_back(d_draws);
+        if (cudaMalloc(&d_stats, stats_bytes) != cudaSuccess) { rc = fail(-42, "cudaMalloc(stats) failed"); break; }
+        to_free.push_back(d_stats);
+        pd.y = d_y; pd.ycst = d_ycst; pd.ntot = d_ntot; pd.xu = d_xu; pd.grp = (const int32_t*)d_grp;
+        pd.rstart = (const int32_t*)d_rstart; pd.U = (const int32_t*)d_U; pd.ref = (const int32_t*)d_ref;
+        pd.lconst = (const double*)d_lconst;
+        sccoda_sampler s2 = *smp;
+        s2.step_begin = 0; s2.step_end = 0; s2.store_draws = 1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        rc = sccoda_sample(&pd, &s2, d_init, d_draws, d_stats, nullptr, st);
+        if (rc) break;
+        cudaEventRecord(e1, st);
+        if (summary) {
+            if (cudaMalloc(&d_sum, B * C * nsum * 8) != cudaSuccess) { rc = fail(-42, "cudaMalloc(summary) failed"); break; }
+            to_free.push_back(d_sum);
+            rc = sccoda_summarize(&pd, (int32_t)S, summary_skip, d_draws, d_stats, (double*)d_sum, st);
+            if (rc) break;
+            cudaMemcpyAsync(summary, d_sum, B * C * nsum * 8, cudaMemcpyDeviceToHost, st);
+        }
+        if (draws) cudaMemcpyAsync(draws, d_draws, draws_bytes, cudaMemcpyDeviceToHost, st);
+        if (stats) cudaMemcpyAsync(stats, d_stats, stats_bytes, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = fail(-44, "kernel/copy failed: %s", cudaGetErrorString(e)); break; }
+        if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cleanup();
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+}  // extern "C"

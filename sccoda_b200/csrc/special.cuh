@@ -1,0 +1,139 @@
+// Special functions for the Dirichlet-multinomial density: digamma / lgamma pieces in fp32 (the
+// production arithmetic: MUFU lg2/ex2/rcp + short FMA polynomials, branch-free) and fp64 (parity build).
+//
+// These replace what TensorFlow's lgamma/digamma kernels and autodiff evaluate for
+// tfd.DirichletMultinomial in /root/reference/sccoda/model/scCODA_model.py:743-751.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace sccoda {
+
+// ----------------------------------------------------------------------------- fp32 primitives
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#define SCCODA_LN2F 0.6931471805599453f
+#define SCCODA_LOG2EF 1.4426950408889634f
+
+__device__ __forceinline__ float log_fast(float x) { return lg2_fast(x) * SCCODA_LN2F; }
+
+// exp with a two-term split of log2(e) so the relative error stays ~2 ulp for |x| up to ~88
+__device__ __forceinline__ float exp_acc(float x) {
+    const float t = x * SCCODA_LOG2EF;
+    const float n = rintf(t);
+    // r = x*log2e - n computed with the product error recovered by fma
+    float r = fmaf(x, SCCODA_LOG2EF, -n);
+    r = fmaf(x, 1.925963033500011e-8f, r);  // low part of log2(e)
+    float p = ex2_fast(r);
+    // scale by 2^n via exponent arithmetic (ex2 of an integer is exact in MUFU, handles under/overflow)
+    return p * ex2_fast(n);
+}
+
+// psi(x), x > 0.  x < 6: psi(x) = psi(x+6) - sum_{i<6} 1/(x+i), the sum evaluated as ONE rational
+// P'(x)/P(x), P(x) = x(x+1)...(x+5) = a(a+4)(a+6), a = x(x+5).  Then the asymptotic series at z >= 6:
+// psi(z) = ln z - 1/(2z) - 1/(12 z^2) + 1/(120 z^4) - 1/(252 z^6)   (next term 1/(240 z^8) < 2.5e-9).
+// Branch-free (selects), 3 MUFU (lg2, rcp, rcp).
+__device__ __forceinline__ float digamma_pos(float x) {
+    const bool small = x < 6.0f;
+    const float a = x * (x + 5.0f);
+    const float P = a * (a + 4.0f) * (a + 6.0f);
+    const float Nn = fmaf(fmaf(3.0f, a, 20.0f), a, 24.0f) * fmaf(2.0f, x, 5.0f);
+    const float corr = small ? Nn * rcp_fast(P) : 0.0f;
+    const float z = small ? x + 6.0f : x;
+    const float w = rcp_fast(z);
+    const float w2 = w * w;
+    const float ser = w2 * fmaf(w2, fmaf(w2, -1.0f / 252.0f, 1.0f / 120.0f), -1.0f / 12.0f);
+    return fmaf(lg2_fast(z), SCCODA_LN2F, fmaf(-0.5f, w, ser)) - corr;
+}
+
+// Variant for arguments known to be >= 6 (e.g. c + y with y >= 6): 2 MUFU.
+__device__ __forceinline__ float digamma_big(float z) {
+    const float w = rcp_fast(z);
+    const float w2 = w * w;
+    const float ser = w2 * fmaf(w2, fmaf(w2, -1.0f / 252.0f, 1.0f / 120.0f), -1.0f / 12.0f);
+    return fmaf(lg2_fast(z), SCCODA_LN2F, fmaf(-0.5f, w, ser));
+}
+
+// Stirling remainder r(z) = lgamma(z) - [(z-1/2) ln z - z + ln(2 pi)/2], z >= 6 (error < 2e-9)
+__device__ __forceinline__ float stirling_rem(float w /* = 1/z */) {
+    const float w2 = w * w;
+    return w * fmaf(w2, fmaf(w2, 1.0f / 1260.0f, -1.0f / 360.0f), 1.0f / 12.0f);
+}
+
+#define SCCODA_HALF_LN_2PI_F 0.9189385332046727f
+
+// lgamma(x), x > 0, fp32: shift by 6 below 6 (minus ln P(x)), Stirling above.
+__device__ __forceinline__ float lgamma_pos(float x) {
+    const bool small = x < 6.0f;
+    const float a = x * (x + 5.0f);
+    const float P = a * (a + 4.0f) * (a + 6.0f);
+    const float z = small ? x + 6.0f : x;
+    const float lz = log_fast(z);
+    const float w = rcp_fast(z);
+    float r = fmaf(z - 0.5f, lz, -z) + SCCODA_HALF_LN_2PI_F + stirling_rem(w);
+    if (small) r -= log_fast(P);
+    return r;
+}
+
+// D(c, y) = lgamma(c + y) - lgamma(y) for a data constant y > 0 (fp32, cancellation-free):
+//   y >= 6:  (y - 1/2) log1p(c/y) + c (ln(c+y) - 1) + r(c+y) - r(y)        [ycst = r(y), host fp64]
+//   y <  6:  lgamma(c+y) - lgamma(y)                                          [ycst = lgamma(y), host fp64]
+// The host packs ycst accordingly (sccoda_b200/_pack.py); magnitude is O(c ln(c+y)) instead of O(y ln y).
+__device__ __forceinline__ float lgamma_shift(float c, float y, float ycst) {
+    const float z = c + y;
+    if (y >= 6.0f) {
+        const float w = rcp_fast(z);
+        const float l1p = log1pf(c * rcp_fast(y));
+        return fmaf(y - 0.5f, l1p, c * (log_fast(z) - 1.0f)) + (stirling_rem(w) - ycst);
+    }
+    return lgamma_pos(z) - ycst;
+}
+
+__device__ __forceinline__ float sigmoid_stable(float s) {
+    // == exp(s)/(1+exp(s)) (scCODA_model.py:724-725) wherever that is finite; no overflow for large |s|
+    const float e = ex2_fast(-fabsf(s) * SCCODA_LOG2EF);
+    const float r = rcp_fast(1.0f + e);
+    return s >= 0.0f ? r : e * r;
+}
+
+// ----------------------------------------------------------------------------- fp64 (parity build)
+__device__ __forceinline__ double digamma_pos(double x) {
+    if (!(x > 0.0)) return (x == 0.0) ? -CUDART_INF : CUDART_NAN;
+    if (isinf(x)) return x;
+    double acc = 0.0;
+    while (x < 10.0) {
+        acc -= 1.0 / x;
+        x += 1.0;
+    }
+    const double w = 1.0 / x, w2 = w * w;
+    const double ser =
+        w2 * (1.0 / 12.0 -
+              w2 * (1.0 / 120.0 -
+                    w2 * (1.0 / 252.0 - w2 * (1.0 / 240.0 - w2 * (1.0 / 132.0 - w2 * (691.0 / 32760.0 - w2 * (1.0 / 12.0)))))));
+    return acc + log(x) - 0.5 * w - ser;
+}
+__device__ __forceinline__ double digamma_big(double z) { return digamma_pos(z); }
+__device__ __forceinline__ double lgamma_pos(double x) { return lgamma(x); }
+// fp64: ycst = 0 and the host constant carries nothing extra — plain lgamma(c+y).
+__device__ __forceinline__ double lgamma_shift(double c, double y, double ycst) { return lgamma(c + y) - ycst; }
+__device__ __forceinline__ double exp_acc(double x) { return exp(x); }
+__device__ __forceinline__ double sigmoid_stable(double s) {
+    const double e = exp(-fabs(s));
+    return s >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
+}
+__device__ __forceinline__ double log_fast(double x) { return log(x); }
+
+}  // namespace sccoda

@@ -1,0 +1,196 @@
+"""
+Device-side engine: owns the packed datasets in HBM (torch tensors are used only as device buffers and for
+the current-stream handle) and drives the C ABI of libsccoda_b200.so.
+
+This is the layer that replaces `CompositionalModel.sampling` -> `tfp.mcmc.sample_chain`
+(sccoda/model/scCODA_model.py:115-169).  It runs B independent datasets x C chains per launch.
+There is no CPU or eager-torch fallback: without a CUDA device or without the native library every entry
+point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _native as nat
+from ._pack import PackedProblem, pack
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("sccoda_b200.engine needs a CUDA device (B200); there is no CPU fallback.")
+    return torch
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+@dataclass
+class SampleOutput:
+    draws: "object"        # torch [B,C,S,P] device
+    stats: "object"        # torch [B,C,S,NSTAT] device
+    carry: "object"        # torch [B,C,P+NCARRY] f64 device
+    kernel_ms: float       # device time of the sampling launch(es), CUDA events
+    warps_per_chain: int
+    chains_per_cta: int
+    grid: int
+    smem_bytes: int
+    launches: int
+
+    def stat(self, name: str):
+        return self.stats[..., nat.STAT_NAMES.index(name)]
+
+
+class DeviceProblem:
+    """B packed datasets resident on one GPU."""
+
+    def __init__(self, packed: PackedProblem, chains: int, device: Optional[int] = None):
+        torch = _torch()
+        self.packed = packed
+        self.C = int(chains)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.tdtype = torch.float32 if packed.dtype == np.float32 else torch.float64
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=False)
+        self.y, self.ycst, self.ntot, self.xu = up(packed.y), up(packed.ycst), up(packed.ntot), up(packed.xu)
+        self.grp, self.rstart, self.U, self.ref = up(packed.grp), up(packed.rstart), up(packed.U), up(packed.ref)
+        self.lconst = up(packed.lconst)
+        self.B, self.N, self.K, self.D, self.P = packed.B, packed.N, packed.K, packed.D, packed.P
+        self.c_problem = nat.Problem(
+            B=self.B, C=self.C, N=self.N, K=self.K, D=self.D, Umax=packed.Umax,
+            dtype=nat.F32 if packed.dtype == np.float32 else nat.F64, reserved=0,
+            y=_ptr(self.y), ycst=_ptr(self.ycst), ntot=_ptr(self.ntot), xu=_ptr(self.xu), grp=_ptr(self.grp),
+            rstart=_ptr(self.rstart), U=_ptr(self.U), ref=_ptr(self.ref), lconst=_ptr(self.lconst))
+
+    @classmethod
+    def from_arrays(cls, x, y, ref, chains: int, dtype=np.float32, device: Optional[int] = None):
+        return cls(pack(x, y, ref, dtype=dtype), chains, device)
+
+    # ------------------------------------------------------------------ K1
+    def logp_grad(self, theta):
+        """theta [B,C,P] (device tensor or array) -> (logp [B,C] f64, grad [B,C,P])."""
+        torch = _torch()
+        theta = torch.as_tensor(theta, dtype=self.tdtype, device=self.device).contiguous()
+        assert tuple(theta.shape) == (self.B, self.C, self.P), theta.shape
+        logp = torch.empty((self.B, self.C), dtype=torch.float64, device=self.device)
+        grad = torch.empty_like(theta)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            nat.check(nat.lib().sccoda_logp_grad(ctypes.byref(self.c_problem), _ptr(theta), _ptr(logp), _ptr(grad),
+                                                 stream), "sccoda_logp_grad")
+        return logp, grad
+
+    # ------------------------------------------------------------------ K2/K3
+    def make_sampler(self, method: int, num_results: int, num_burnin: int, num_adapt: Optional[int] = None,
+                     num_leapfrog: int = 10, max_tree_depth: int = 10, step_size: float = 0.01,
+                     target_accept: float = 0.75, seed: int = 0, chain_id0: int = 0,
+                     warps_per_chain: int = 0) -> nat.Sampler:
+        if num_adapt is None:
+            num_adapt = int(0.8 * num_burnin)            # scCODA_model.py:284-285
+        return nat.Sampler(method=method, num_results=num_results, num_burnin=num_burnin, num_adapt=num_adapt,
+                           num_leapfrog=num_leapfrog, max_tree_depth=max_tree_depth, step_begin=0, step_end=0,
+                           step_size=step_size, target_accept=target_accept, seed=seed, chain_id0=chain_id0,
+                           warps_per_chain=warps_per_chain, store_draws=1, reserved=0)
+
+    def plan(self, smp: nat.Sampler):
+        w, c, g, s = (ctypes.c_int32() for _ in range(4))
+        nat.check(nat.lib().sccoda_launch_plan(ctypes.byref(self.c_problem), ctypes.byref(smp), ctypes.byref(w),
+                                               ctypes.byref(c), ctypes.byref(g), ctypes.byref(s)), "sccoda_launch_plan")
+        return w.value, c.value, g.value, s.value
+
+    def sample(self, init, smp: nat.Sampler, chunk: Optional[int] = None, progress=None,
+               draws=None, stats=None) -> SampleOutput:
+        """Run the whole chain (one persistent launch, or `chunk`-step launches with resume through `carry`)."""
+        torch = _torch()
+        init = torch.as_tensor(init, dtype=self.tdtype, device=self.device).contiguous()
+        assert tuple(init.shape) == (self.B, self.C, self.P), (init.shape, (self.B, self.C, self.P))
+        S = smp.num_results
+        if draws is None:
+            draws = torch.empty((self.B, self.C, S, self.P), dtype=self.tdtype, device=self.device)
+        if stats is None:
+            stats = torch.empty((self.B, self.C, S, nat.NSTAT), dtype=self.tdtype, device=self.device)
+        carry = torch.zeros((self.B, self.C, self.P + nat.NCARRY), dtype=torch.float64, device=self.device)
+        total = smp.num_burnin + smp.num_results
+        chunk = total if not chunk else int(chunk)
+        w, cpc, grid, smem = self.plan(smp)
+        launches = 0
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            begin = 0
+            while begin < total:
+                end = min(total, begin + chunk)
+                smp.step_begin, smp.step_end = begin, end
+                nat.check(nat.lib().sccoda_sample(ctypes.byref(self.c_problem), ctypes.byref(smp), _ptr(init),
+                                                  _ptr(draws), _ptr(stats), _ptr(carry), stream.cuda_stream),
+                          "sccoda_sample")
+                launches += 1
+                begin = end
+                if progress is not None:
+                    stream.synchronize()
+                    progress(end, total)
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+        smp.step_begin, smp.step_end = 0, 0
+        return SampleOutput(draws=draws, stats=stats, carry=carry, kernel_ms=ms, warps_per_chain=w,
+                            chains_per_cta=cpc, grid=grid, smem_bytes=smem, launches=launches)
+
+    # ------------------------------------------------------------------ K4
+    def summary_width(self) -> int:
+        return nat.NSUM_PARAM * self.P + nat.NSUM_BETA * self.D * self.K + nat.NSUM_SCALAR
+
+    def summarize(self, draws, stats, skip: int):
+        """Per-chain summaries [B,C,width] f64 on device (layout: include/sccoda_b200.h)."""
+        torch = _torch()
+        S = draws.shape[2]
+        out = torch.empty((self.B, self.C, self.summary_width()), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            nat.check(nat.lib().sccoda_summarize(ctypes.byref(self.c_problem), S, int(skip), _ptr(draws), _ptr(stats),
+                                                 _ptr(out), stream), "sccoda_summarize")
+        return out
+
+    def split_summary(self, summ):
+        """summary tensor/array [B,C,width] -> dict of named views."""
+        P, DK = self.P, self.D * self.K
+        o = 0
+        out = {}
+        for name, n in (("mean", P), ("m2", P), ("inc_count", DK), ("inc_sum", DK), ("beta_mean", DK),
+                        ("beta_m2", DK)):
+            out[name] = summ[..., o:o + n]
+            o += n
+        for i, name in enumerate(("n_used", "n_accepted", "sum_accept_prob", "leapfrogs", "n_diverging",
+                                  "last_step_size")):
+            out[name] = summ[..., o + i]
+        return out
+
+
+def sample_host(packed: PackedProblem, chains: int, init: np.ndarray, smp: nat.Sampler, want_draws: bool = True,
+                want_summary: bool = False, summary_skip: int = 0, device: int = 0):
+    """End-to-end call with HOST buffers through sccoda_sample_host (copies inside the native call)."""
+    dt = packed.dtype
+    B, C, S, P = packed.B, int(chains), smp.num_results, packed.P
+    init = np.ascontiguousarray(init, dtype=dt)
+    assert init.shape == (B, C, P)
+    prob = nat.Problem(B=B, C=C, N=packed.N, K=packed.K, D=packed.D, Umax=packed.Umax,
+                       dtype=nat.F32 if dt == np.float32 else nat.F64, reserved=0,
+                       y=packed.y.ctypes.data, ycst=packed.ycst.ctypes.data, ntot=packed.ntot.ctypes.data,
+                       xu=packed.xu.ctypes.data, grp=packed.grp.ctypes.data, rstart=packed.rstart.ctypes.data,
+                       U=packed.U.ctypes.data, ref=packed.ref.ctypes.data, lconst=packed.lconst.ctypes.data)
+    draws = np.empty((B, C, S, P), dtype=dt) if want_draws else None
+    stats = np.empty((B, C, S, nat.NSTAT), dtype=dt) if want_draws else None
+    width = nat.NSUM_PARAM * P + nat.NSUM_BETA * packed.D * packed.K + nat.NSUM_SCALAR
+    summ = np.empty((B, C, width), dtype=np.float64) if want_summary else None
+    ms = ctypes.c_float(0.0)
+    nat.check(nat.lib().sccoda_sample_host(
+        ctypes.byref(prob), ctypes.byref(smp), init.ctypes.data,
+        draws.ctypes.data if draws is not None else None, stats.ctypes.data if stats is not None else None,
+        summ.ctypes.data if summ is not None else None, int(summary_skip), int(device), ctypes.byref(ms)),
+        "sccoda_sample_host")
+    return draws, stats, summ, float(ms.value)
