@@ -33,7 +33,7 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
     const size_t NK = (size_t)N * K, UK = (size_t)Umax * K, P = (size_t)D + 2 * (size_t)D * (K - 1) + K;
     size_t o = 0;
     p.y = o; o += rnd16(NK * ts);
-    p.ycst = o; o += rnd16(NK * ts);
+    p.ycst = o; o += (ts == 4) ? rnd16(NK * ts) : 0;  // fp64 build: the constant is identically 0, not staged
     p.ntot = o; o += rnd16((size_t)N * ts);
     p.xu = o; o += rnd16((size_t)Umax * D * ts);
     p.grp = o; o += rnd16((size_t)N * 4);
@@ -84,7 +84,7 @@ __device__ __forceinline__ void stage_dataset(const KArgs& a, int b, unsigned ch
     int* grp = reinterpret_cast<int*>(smem + pl.grp);
     int* rstart = reinterpret_cast<int*>(smem + pl.rstart);
     copy_to_smem(y, static_cast<const T*>(a.y) + (size_t)b * N * K, N * K);
-    copy_to_smem(ycst, static_cast<const T*>(a.ycst) + (size_t)b * N * K, N * K);
+    if (sizeof(T) == 4) copy_to_smem(ycst, static_cast<const T*>(a.ycst) + (size_t)b * N * K, N * K);
     copy_to_smem(ntot, static_cast<const T*>(a.ntot) + (size_t)b * N, N);
     copy_to_smem(xu, static_cast<const T*>(a.xu) + (size_t)b * Umax * D, Umax * D);
     copy_to_smem(grp, a.grp + (size_t)b * N, N);

@@ -172,7 +172,7 @@ __device__ __forceinline__ double dm_eval(const Dims& dm, const DataTile<T>& dt,
             const T psi = big ? digamma_big(z) : digamma_pos(z);
             if (valid) {
                 cs.G[e] = c * (psi - cs.psic[uk] - cs.rowterm[n]);
-                if (WITH_LOGP) lp += (double)lgamma_shift(c, yv, dt.ycst[e]);
+                if (WITH_LOGP) lp += (double)lgamma_shift(c, yv, sizeof(T) == 4 ? dt.ycst[e] : T(0));
             }
         }
     }
