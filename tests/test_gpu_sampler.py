@@ -1,0 +1,206 @@
+"""K2/K3 parity: the persistent HMC / NUTS kernels (through the C ABI) vs the CPU oracle.
+
+* fp64 build, same Philox streams  -> the device chain must walk the oracle's trajectory (until chaotic
+  amplification of summation-order rounding, so the windows are short for the aggressive adapters).
+* fp32 build -> statistical agreement over many chains (accept rate, step size, posterior means, inclusion).
+"""
+import numpy as np
+import pytest
+
+from conftest import haber_salm, synthetic_dataset
+
+pytestmark = pytest.mark.gpu
+
+
+def _init(rs, D, K, n):
+    out = np.zeros((n, D + 2 * D * (K - 1) + K))
+    out[:, :D] = 1.0                                           # scCODA_model.py:763-768
+    out[:, D:D + D * (K - 1)] = rs.randn(n, D * (K - 1))
+    out[:, -K:] = rs.randn(n, K)
+    return out
+
+
+def _oracle_run(x, y, ref, init, method, nr, nb, **kw):
+    from oracle import c_oracle, np_oracle as o
+    m = o.prepare(x, y, ref)
+    return c_oracle.sample(m.x[None], m.y[None], m.n_total[None], [m.logp_const], [m.ref], init[None], method, nr, nb,
+                           **kw)
+
+
+@pytest.mark.parametrize("method,steps,tol", [(0, 40, 1e-9), (1, 8, 1e-7), (2, 6, 1e-6)])
+@pytest.mark.parametrize("W", [1, 2, 4])
+def test_fp64_trajectory_follows_oracle(method, steps, tol, W):
+    from sccoda_b200.engine import DeviceProblem
+    x, y, _ = haber_salm()
+    init = _init(np.random.RandomState(0), 1, 8, 3)
+    d_ref, s_ref = _oracle_run(x, y, 5, init, method, steps, 0, num_adapt=steps, seed=7, chain_id0=3)
+    prob = DeviceProblem.from_arrays(x, y, 5, chains=3, dtype=np.float64)
+    smp = prob.make_sampler(method, steps, 0, num_adapt=steps, seed=7, chain_id0=3, warps_per_chain=W)
+    out = prob.sample(init[None], smp)
+    d = out.draws.cpu().numpy()
+    assert np.abs(d - d_ref).max() < tol
+    for name in ("leapfrogs_taken", "is_accepted", "diverging", "reach_max_depth"):
+        assert np.array_equal(out.stat(name).cpu().numpy(), s_ref[name]), name
+    assert np.allclose(out.stat("step_size").cpu().numpy(), s_ref["step_size"], rtol=1e-9)
+    assert np.allclose(out.stat("target_log_prob").cpu().numpy(), s_ref["target_log_prob"], rtol=1e-9, atol=1e-7)
+    fin = np.isfinite(s_ref["log_accept_ratio"])
+    assert np.allclose(out.stat("log_accept_ratio").cpu().numpy()[fin], s_ref["log_accept_ratio"][fin], atol=1e-6)
+
+
+def test_fp64_trajectory_synthetic_multi_covariate():
+    """D=3 covariates (U=8 groups after packing), K=9: exercises the grouped layout against the plain oracle."""
+    from sccoda_b200.engine import DeviceProblem
+    x, y = synthetic_dataset(5, N=12, K=9, D=3)
+    y[0, 0] = 0
+    init = _init(np.random.RandomState(1), 3, 9, 2)
+    d_ref, s_ref = _oracle_run(x, y, 2, init, 0, 30, 10, num_adapt=30, seed=5, chain_id0=0)
+    prob = DeviceProblem.from_arrays(x, y, 2, chains=2, dtype=np.float64)
+    out = prob.sample(init[None], prob.make_sampler(0, 30, 10, num_adapt=30, seed=5))
+    assert np.abs(out.draws.cpu().numpy() - d_ref).max() < 1e-8
+
+
+def test_chunked_resume_is_bit_identical():
+    from sccoda_b200.engine import DeviceProblem
+    x, y, _ = haber_salm()
+    init = _init(np.random.RandomState(2), 1, 8, 2)
+    for method, nr, nb in ((0, 60, 40), (1, 60, 40), (2, 12, 8)):
+        prob = DeviceProblem.from_arrays(x, y, 5, chains=2, dtype=np.float64)
+        one = prob.sample(init[None], prob.make_sampler(method, nr, nb, seed=3))
+        many = prob.sample(init[None], prob.make_sampler(method, nr, nb, seed=3), chunk=7)
+        assert many.launches > 1
+        assert np.array_equal(one.draws.cpu().numpy(), many.draws.cpu().numpy()), method
+        assert np.array_equal(one.stats.cpu().numpy(), many.stats.cpu().numpy(), equal_nan=True), method
+
+
+def test_chain_streams_are_independent_of_sharding():
+    """chain_id0 offsets: running chains [0,4) at once equals running [0,2) and [2,4) separately (multi-GPU sharding)."""
+    from sccoda_b200.engine import DeviceProblem
+    x, y, _ = haber_salm()
+    init = _init(np.random.RandomState(4), 1, 8, 4)
+    full = DeviceProblem.from_arrays(x, y, 5, chains=4, dtype=np.float64)
+    d_full = full.sample(init[None], full.make_sampler(0, 30, 10, seed=9)).draws.cpu().numpy()
+    half = DeviceProblem.from_arrays(x, y, 5, chains=2, dtype=np.float64)
+    d_a = half.sample(init[None, :2], half.make_sampler(0, 30, 10, seed=9, chain_id0=0)).draws.cpu().numpy()
+    d_b = half.sample(init[None, 2:], half.make_sampler(0, 30, 10, seed=9, chain_id0=2)).draws.cpu().numpy()
+    assert np.array_equal(d_full[:, :2], d_a) and np.array_equal(d_full[:, 2:], d_b)
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_fp32_statistical_parity_haber(method):
+    """64 fp32 device chains vs 64 fp64 oracle chains on Haber/Salmonella, sample_hmc(_da) semantics.
+
+    Tolerances are Monte-Carlo tolerances: means over 64 chains; per-chain sd taken from the oracle sample."""
+    from sccoda_b200.engine import DeviceProblem
+    x, y, _ = haber_salm()
+    C, nr, nb = 64, 3000, 1500
+    init = _init(np.random.RandomState(7), 1, 8, C)
+    d_ref, s_ref = _oracle_run(x, y, 5, init, method, nr, nb, seed=21, chain_id0=0)
+    prob = DeviceProblem.from_arrays(x, y, 5, chains=C, dtype=np.float32)
+    out = prob.sample(init[None], prob.make_sampler(method, nr, nb, seed=22))
+    d = out.draws.double().cpu().numpy()
+    assert np.isfinite(d).all()
+
+    def chain_stat(a):          # per-chain acceptance etc. -> mean and standard error over chains
+        return a.mean(), a.std(ddof=1) / np.sqrt(len(a))
+
+    # acceptance rate and adapted step size
+    acc, acc_se = chain_stat(out.stat("is_accepted").double().cpu().numpy()[0].mean(1))
+    acc_r, acc_r_se = chain_stat(s_ref["is_accepted"][0].mean(1))
+    assert abs(acc - acc_r) < 5 * np.hypot(acc_se, acc_r_se) + 0.01, (acc, acc_r)
+    eps, eps_se = chain_stat(out.stat("step_size").double().cpu().numpy()[0][:, -1])
+    eps_r, eps_r_se = chain_stat(s_ref["step_size"][0][:, -1])
+    assert abs(eps - eps_r) < 5 * np.hypot(eps_se, eps_r_se) + 0.002, (eps, eps_r)
+    # posterior means of the intercepts (alpha): chain means are ~independent replicates
+    K = 8
+    am, ar = d[0, :, nb // 2:, -K:].mean(1), d_ref[0, :, nb // 2:, -K:].mean(1)
+    se = np.hypot(am.std(0, ddof=1), ar.std(0, ddof=1)) / np.sqrt(C)
+    assert np.all(np.abs(am.mean(0) - ar.mean(0)) < 5 * se + 0.02), (am.mean(0), ar.mean(0))
+    # inclusion probability of the strong Enterocyte effect (k=1) and of a null effect (k=0)
+    def inclusion(dr):
+        sig, boff, iraw = dr[..., 0:1], dr[..., 1:8], dr[..., 8:15]
+        beta = 1 / (1 + np.exp(-50 * iraw)) * sig * boff
+        return (np.abs(beta) > 1e-3).mean(-2)               # [chains, K-1]
+    inc, inc_r = inclusion(d[0, :, nb // 2:]), inclusion(d_ref[0, :, nb // 2:])
+    se = np.hypot(inc.std(0, ddof=1), inc_r.std(0, ddof=1)) / np.sqrt(C)
+    assert np.all(np.abs(inc.mean(0) - inc_r.mean(0)) < 5 * se + 0.03), (inc.mean(0), inc_r.mean(0))
+    assert inc.mean(0)[1] > 0.9                              # Enterocyte is credible in every tutorial run
+
+
+def test_fp32_statistical_parity_nuts():
+    from sccoda_b200.engine import DeviceProblem
+    x, y, _ = haber_salm()
+    C, nr, nb = 32, 400, 300
+    init = _init(np.random.RandomState(8), 1, 8, C)
+    d_ref, s_ref = _oracle_run(x, y, 5, init, 2, nr, nb, seed=31, chain_id0=0, max_tree_depth=8)
+    prob = DeviceProblem.from_arrays(x, y, 5, chains=C, dtype=np.float32)
+    out = prob.sample(init[None], prob.make_sampler(2, nr, nb, seed=32, max_tree_depth=8))
+    d = out.draws.double().cpu().numpy()
+    assert np.isfinite(d).all()
+    lf, lf_r = out.stat("leapfrogs_taken").double().cpu().numpy()[0].mean(1), s_ref["leapfrogs_taken"][0].mean(1)
+    assert abs(np.log(lf.mean() / lf_r.mean())) < 0.35, (lf.mean(), lf_r.mean())
+    a = np.exp(np.minimum(out.stat("log_accept_ratio").double().cpu().numpy()[0], 0)).mean()
+    a_r = np.exp(np.minimum(s_ref["log_accept_ratio"][0], 0)).mean()
+    assert abs(a - a_r) < 0.08, (a, a_r)
+    am, ar = d[0, :, :, -8:].mean(1), d_ref[0, :, :, -8:].mean(1)
+    se = np.hypot(am.std(0, ddof=1), ar.std(0, ddof=1)) / np.sqrt(C)
+    assert np.all(np.abs(am.mean(0) - ar.mean(0)) < 5 * se + 0.05), (am.mean(0), ar.mean(0))
+
+
+def test_summary_kernel_matches_numpy():
+    """K4 vs the numpy restatement of get_y_hat / complete_beta_df arithmetic on the same draws."""
+    from oracle import np_oracle as o
+    from sccoda_b200.engine import DeviceProblem
+    x, y = synthetic_dataset(3, N=10, K=6, D=2)
+    C, nr, nb, skip = 3, 500, 200, 150
+    init = _init(np.random.RandomState(9), 2, 6, C)
+    prob = DeviceProblem.from_arrays(x, y, 4, chains=C, dtype=np.float32)
+    out = prob.sample(init[None], prob.make_sampler(0, nr, nb, seed=5))
+    s = prob.split_summary(prob.summarize(out.draws, out.stats, skip).cpu().numpy())
+    d = out.draws.double().cpu().numpy()[0]
+    m = o.prepare(x, y, 4)
+    for c in range(C):
+        used = d[c, skip:]
+        assert np.allclose(s["mean"][0, c], used.mean(0), rtol=1e-6, atol=1e-7)
+        assert np.allclose(s["m2"][0, c], ((used - used.mean(0)) ** 2).sum(0), rtol=1e-5, atol=1e-6)
+        der, _ = o.derived_draws(used, m)
+        beta = der["beta"].reshape(len(used), -1)
+        inc = (np.abs(beta) > 1e-3)
+        assert np.abs(s["inc_count"][0, c] - inc.sum(0)).max() <= 2          # |beta| ~ 1e-3 ties in fp32
+        assert np.allclose(s["beta_mean"][0, c], beta.mean(0), atol=1e-5)
+        assert np.allclose(s["inc_sum"][0, c], (beta * inc).sum(0), atol=5e-3)
+        assert s["n_used"][0, c] == nr - skip
+        assert s["n_accepted"][0, c] == out.stat("is_accepted")[0, c].sum().item()
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    """sccoda_sample_host (host pointers, copies inside) == the device-pointer path, bit for bit."""
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem, sample_host
+    x, y, _ = haber_salm()
+    pk = pack(x, y, 5, dtype=np.float32)
+    init = _init(np.random.RandomState(3), 1, 8, 4).astype(np.float32)
+    prob = DeviceProblem(pk, chains=4)
+    smp = prob.make_sampler(1, 200, 100, seed=17)
+    out = prob.sample(init[None], smp)
+    summ_dev = prob.summarize(out.draws, out.stats, 50).cpu().numpy()
+    draws, stats, summ, ms = sample_host(pk, 4, init[None], prob.make_sampler(1, 200, 100, seed=17),
+                                         want_draws=True, want_summary=True, summary_skip=50)
+    assert ms > 0
+    assert np.array_equal(draws, out.draws.cpu().numpy())
+    assert np.array_equal(stats, out.stats.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(summ, summ_dev)
+
+
+def test_diverging_flag_and_negative_sigma_rejection():
+    """A huge step size throws proposals into sigma_d < 0 / overflow: they must be rejected, flagged and finite."""
+    from sccoda_b200.engine import DeviceProblem
+    x, y, _ = haber_salm()
+    init = _init(np.random.RandomState(5), 1, 8, 8)
+    prob = DeviceProblem.from_arrays(x, y, 5, chains=8, dtype=np.float32)
+    out = prob.sample(init[None], prob.make_sampler(0, 200, 0, num_adapt=0, step_size=0.8, seed=1))
+    assert np.isfinite(out.draws.cpu().numpy()).all()
+    lar = out.stat("log_accept_ratio").cpu().numpy()
+    div = out.stat("diverging").cpu().numpy()
+    assert np.array_equal(div == 1, lar < -1000)                          # scCODA_model.py:299
+    acc = out.stat("is_accepted").cpu().numpy()
+    assert acc[lar == -np.inf].sum() == 0

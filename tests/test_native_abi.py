@@ -1,0 +1,109 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/sccoda_b200.h declares; struct layouts and
+argument validation behave (no kernel is launched here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, synthetic_dataset
+from sccoda_b200 import _native as nat
+from sccoda_b200._pack import pack
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "sccoda_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sccoda_[a-z_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = nat.lib()
+    names = _declared_functions()
+    assert set(names) == set(nat.EXPORTS), (names, nat.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.sccoda_version() >= 100
+
+
+def test_header_constants_match_binding():
+    src = open(os.path.join(ROOT, "include", "sccoda_b200.h")).read()
+    consts = dict(re.findall(r"#define\s+(SCCODA_[A-Z0-9_]+)\s+(\d+)", src))
+    assert int(consts["SCCODA_NSTAT"]) == nat.NSTAT == len(nat.STAT_NAMES)
+    assert int(consts["SCCODA_NCARRY"]) == nat.NCARRY
+    assert int(consts["SCCODA_NSUM_PARAM"]) == nat.NSUM_PARAM
+    assert int(consts["SCCODA_NSUM_BETA"]) == nat.NSUM_BETA
+    assert int(consts["SCCODA_NSUM_SCALAR"]) == nat.NSUM_SCALAR
+    for i, name in enumerate(nat.STAT_NAMES):
+        key = "SCCODA_ST_" + name.upper()
+        assert int(consts[key]) == i, key
+
+
+def _problem(pk, C):
+    return nat.Problem(B=pk.B, C=C, N=pk.N, K=pk.K, D=pk.D, Umax=pk.Umax, dtype=nat.F32, reserved=0,
+                       y=pk.y.ctypes.data, ycst=pk.ycst.ctypes.data, ntot=pk.ntot.ctypes.data, xu=pk.xu.ctypes.data,
+                       grp=pk.grp.ctypes.data, rstart=pk.rstart.ctypes.data, U=pk.U.ctypes.data,
+                       ref=pk.ref.ctypes.data, lconst=pk.lconst.ctypes.data)
+
+
+def _sampler(**kw):
+    d = dict(method=0, num_results=100, num_burnin=50, num_adapt=40, num_leapfrog=10, max_tree_depth=10, step_begin=0,
+             step_end=0, step_size=0.01, target_accept=0.75, seed=1, chain_id0=0, warps_per_chain=0, store_draws=1,
+             reserved=0)
+    d.update(kw)
+    return nat.Sampler(**d)
+
+
+def _plan(prob, smp):
+    w, c, g, s = (ctypes.c_int32() for _ in range(4))
+    rc = nat.lib().sccoda_launch_plan(ctypes.byref(prob), ctypes.byref(smp), *(ctypes.byref(v) for v in (w, c, g, s)))
+    return rc, w.value, c.value, g.value, s.value
+
+
+def test_launch_plan_sweep_config():
+    """1024 datasets x 4 chains, K=N=20: one warp per chain, the 4 chains of a dataset share one CTA."""
+    x, y = synthetic_dataset(0)
+    pk = pack(np.broadcast_to(x, (1024,) + x.shape), np.broadcast_to(y, (1024,) + y.shape), 19)
+    rc, w, cpc, grid, smem = _plan(_problem(pk, 4), _sampler())
+    assert rc == 0 and w == 1 and cpc == 4 and grid == 1024 and 0 < smem < 48 * 1024
+
+
+def test_launch_plan_scales_warps_for_few_chains_and_big_models():
+    x, y = synthetic_dataset(0, N=200, K=50, D=4)
+    pk = pack(x, y, 49)
+    rc, w, cpc, grid, smem = _plan(_problem(pk, 64), _sampler(method=2))
+    assert rc == 0 and w == 16 and cpc == 1 and grid == 64 and smem <= 227 * 1024
+    x, y = synthetic_dataset(0, N=10, K=5)
+    pk = pack(x, y, 4)
+    rc, w, cpc, grid, smem = _plan(_problem(pk, 1), _sampler())
+    assert rc == 0 and w == 2 and grid == 1
+
+
+@pytest.mark.parametrize("kw,code", [(dict(method=7), -11), (dict(num_results=0), -12), (dict(num_leapfrog=0), -13),
+                                      (dict(method=2, max_tree_depth=0), -14), (dict(step_size=0.0), -15),
+                                      (dict(step_begin=10, step_end=5), -16), (dict(warps_per_chain=3), -8)])
+def test_sampler_validation(kw, code):
+    x, y = synthetic_dataset(0)
+    pk = pack(x, y, 19)
+    rc, *_ = _plan(_problem(pk, 4), _sampler(**kw))
+    assert rc == code
+    assert len(nat.lib().sccoda_last_error()) > 0
+
+
+def test_problem_validation():
+    x, y = synthetic_dataset(0)
+    pk = pack(x, y, 19)
+    p = _problem(pk, 4)
+    p.K = 1
+    assert _plan(p, _sampler())[0] == -3
+    p = _problem(pk, 0)
+    assert _plan(p, _sampler())[0] == -2
+    p = _problem(pk, 4)
+    p.y = None
+    assert _plan(p, _sampler())[0] == -7
+
+
+def test_check_raises_runtime_error():
+    with pytest.raises(RuntimeError, match="failed"):
+        nat.check(-3, "unit-test")
