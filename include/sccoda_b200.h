@@ -133,6 +133,10 @@ int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, in
 int sccoda_sample_host(const sccoda_problem* prob_host, const sccoda_sampler* smp, const void* init, void* draws,
                        void* stats, double* summary, int32_t summary_skip, int32_t device, float* kernel_ms);
 
+/* Measurement utility for the bench: FP32 FFMA peak (TFLOP/s, 2 flop per FMA) and MUFU peak (T op/s) of the
+ * current device, from two register-resident micro-kernels (best of 5). Synchronises `stream`. */
+int sccoda_measure_peaks(float* fp32_tflops, float* mufu_tops, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,23 @@ def u01(word: int) -> float:
     return ((word >> 8) + 0.5) * (1.0 / 16777216.0)
 
 
+class FastRNG:
+    """numpy Generator with the ChainRNG interface — NOT the device contract; used only when the oracle is
+    *timed* as the CPU baseline, so that the pure-python Philox does not inflate the baseline's run time."""
+
+    def __init__(self, seed: int, chain: int):
+        self.g = np.random.default_rng([seed, chain])
+
+    def normals(self, n: int, step: int) -> np.ndarray:
+        return self.g.standard_normal(n)
+
+    def uniform(self, index: int, step: int, stream: int) -> float:
+        return float(self.g.random())
+
+    def bit(self, index: int, step: int, stream: int) -> int:
+        return int(self.g.integers(2))
+
+
 class ChainRNG:
     """Counter-based draws for one chain; mirrors the device functions one to one."""
 
@@ -390,7 +407,8 @@ def nuts_transition(theta, lp, g, eps, max_depth, m, rng: ChainRNG, step, max_en
 
 def sample_chain(m: ModelData, init: np.ndarray, method: int, num_results: int, num_burnin: int,
                  num_adapt: int | None = None, num_leapfrog: int = 10, max_tree_depth: int = 10,
-                 step_size: float = 0.01, seed: int = 0, chain: int = 0, target_accept: float = 0.75):
+                 step_size: float = 0.01, seed: int = 0, chain: int = 0, target_accept: float = 0.75,
+                 fast_rng: bool = False):
     """tfp.mcmc.sample_chain as driven by CompositionalModel.sampling (scCODA_model.py:152-161).
 
     Runs num_burnin + num_results transitions, traces the last num_results (the python-side second
@@ -398,7 +416,7 @@ def sample_chain(m: ModelData, init: np.ndarray, method: int, num_results: int, 
     """
     if num_adapt is None:
         num_adapt = int(0.8 * num_burnin)                     # :284-285
-    rng = ChainRNG(seed, chain)
+    rng = FastRNG(seed, chain) if fast_rng else ChainRNG(seed, chain)
     theta = np.array(init, dtype=np.float64)
     lp, g = logp(theta, m), grad(theta, m)
     P = theta.shape[0]

@@ -20,7 +20,7 @@ NCARRY = 8
 NSUM_PARAM, NSUM_BETA, NSUM_SCALAR = 2, 4, 6
 
 EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sample", "sccoda_summarize",
-           "sccoda_launch_plan", "sccoda_sample_host")
+           "sccoda_launch_plan", "sccoda_sample_host", "sccoda_measure_peaks")
 
 
 class Problem(ctypes.Structure):
@@ -63,6 +63,7 @@ def lib() -> ctypes.CDLL:
         _lib.sccoda_summarize.argtypes = [pp, i32, i32, vp, vp, vp, vp]
         _lib.sccoda_launch_plan.argtypes = [pp, sp] + [ctypes.POINTER(i32)] * 4
         _lib.sccoda_sample_host.argtypes = [pp, sp, vp, vp, vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float)]
+        _lib.sccoda_measure_peaks.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), vp]
     return _lib
 
 
