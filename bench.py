@@ -191,6 +191,9 @@ class ClockSampler:
                 "power_w_max": float(max(power)) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+PACKED_DEVICE_FIELDS = ("ey", "eycst", "eidx", "colperm", "nbig", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -210,7 +213,7 @@ def pinned_copy(packed):
         keep.append(t)
         return t.numpy()
     fields = {f.name: getattr(packed, f.name) for f in dataclasses.fields(packed)}
-    for k in ("y", "ycst", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst"):
+    for k in PACKED_DEVICE_FIELDS:
         fields[k] = pin(fields[k])
     return type(packed)(**fields), keep
 
@@ -359,7 +362,7 @@ def run_ours(a):
         torch.cuda.empty_cache()
         pk_pin, keep = pinned_copy(packed)
         init_pin = torch.from_numpy(init).pin_memory()
-        h2d = sum(getattr(pk_pin, k).nbytes for k in ("y", "ycst", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst"))
+        h2d = sum(getattr(pk_pin, k).nbytes for k in PACKED_DEVICE_FIELDS)
         h2d += init_pin.numel() * 4
         width = nat.NSUM_PARAM * P + nat.NSUM_BETA * D * K + nat.NSUM_SCALAR
         d2h = B * C * width * 8

@@ -23,9 +23,14 @@
  *   - return value: 0 on success, negative error code otherwise; sccoda_last_error() gives the text.
  *   - thread-compatible, not thread-safe: one host thread per device context.
  *
- * Packed dataset layout (built by sccoda_b200/_pack.py or by the caller; B datasets of equal shape):
- *   y       [B,N,K]     counts after the 0.5 pseudocount (scCODA_model.py:94-96), rows sorted by covariate group
- *   ycst    [B,N,K]     per-count constant: fp32 -> r(y) if y>=6 else lgamma(y); fp64 -> 0   (see csrc/special.cuh)
+ * Packed dataset layout (built by sccoda_b200/_pack.py or by the caller; B datasets of equal shape).
+ * Rows are sorted by covariate group; the N*K counts form an "element list" stored column-major with the
+ * columns (cell types) sorted by decreasing minimum count: element e = kk*N + n.
+ *   ey      [B,N*K]     counts after the 0.5 pseudocount (scCODA_model.py:94-96), element-list order
+ *   eycst   [B,N*K]     per-count constant: fp32 -> r(y) if y>=6 else lgamma(y); fp64 -> 0   (see csrc/special.cuh)
+ *   eidx    [B,N*K] u32 packed index (u*K + k) | (n << 16): covariate group u, ORIGINAL cell type k, row n
+ *   colperm [B,K] i32   sorted column position kk -> original cell type k
+ *   nbig    [B] i32     the first nbig elements have counts >= 6 (N * number of columns whose minimum is >= 6)
  *   ntot    [B,N]       row sums of y (scCODA_model.py:99-100)
  *   xu      [B,Umax,D]  unique covariate rows (design matrix without intercept, comp_ana.py:73-75)
  *   grp     [B,N] i32   covariate group of each row, non-decreasing
@@ -77,9 +82,12 @@ typedef struct sccoda_problem {
     int32_t B, C;          /* datasets, chains per dataset */
     int32_t N, K, D, Umax; /* samples, cell types, covariates, max covariate groups */
     int32_t dtype;         /* SCCODA_F32 / SCCODA_F64 */
-    int32_t reserved;
-    const void* y;
-    const void* ycst;
+    int32_t nbig_min;      /* min over datasets of nbig[b] (host copy; sizes the shared-memory fallback loop) */
+    const void* ey;
+    const void* eycst;
+    const uint32_t* eidx;
+    const int32_t* colperm;
+    const int32_t* nbig;
     const void* ntot;
     const void* xu;
     const int32_t* grp;

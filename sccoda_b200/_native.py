@@ -26,8 +26,10 @@ EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sa
 class Problem(ctypes.Structure):
     _fields_ = [("B", ctypes.c_int32), ("C", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
                 ("D", ctypes.c_int32), ("Umax", ctypes.c_int32), ("dtype", ctypes.c_int32),
-                ("reserved", ctypes.c_int32),
-                ("y", ctypes.c_void_p), ("ycst", ctypes.c_void_p), ("ntot", ctypes.c_void_p), ("xu", ctypes.c_void_p),
+                ("nbig_min", ctypes.c_int32),
+                ("ey", ctypes.c_void_p), ("eycst", ctypes.c_void_p), ("eidx", ctypes.c_void_p),
+                ("colperm", ctypes.c_void_p), ("nbig", ctypes.c_void_p),
+                ("ntot", ctypes.c_void_p), ("xu", ctypes.c_void_p),
                 ("grp", ctypes.c_void_p), ("rstart", ctypes.c_void_p), ("U", ctypes.c_void_p),
                 ("ref", ctypes.c_void_p), ("lconst", ctypes.c_void_p)]
 

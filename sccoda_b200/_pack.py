@@ -3,8 +3,10 @@ Host-side packer: raw (x, y, reference) -> the packed dataset layout of include/
 
 Mirrors the input handling of CompositionalModel.__init__ (sccoda/model/scCODA_model.py:90-100): counts are
 cast to float64, zeros are replaced by a 0.5 pseudocount BEFORE the row sums are taken.  Rows are then sorted
-by covariate group (rows with identical covariate vectors share their concentrations, see csrc/model.cuh) and
-every parameter-independent term of the log-density is folded into one float64 constant per dataset.
+by covariate group (rows with identical covariate vectors share their concentrations, see csrc/model.cuh), the
+counts are laid out as a column-major "element list" with the cell types sorted by decreasing minimum count
+(so that the elements whose digamma needs no recurrence shift come first), and every parameter-independent
+term of the log-density is folded into one float64 constant per dataset.
 """
 from __future__ import annotations
 
@@ -26,8 +28,13 @@ class PackedProblem:
     D: int
     Umax: int
     dtype: np.dtype
-    y: np.ndarray        # [B,N,K]
-    ycst: np.ndarray     # [B,N,K]
+    ey: np.ndarray       # [B,N*K]   counts, element-list order (e = kk*N + n)
+    eycst: np.ndarray    # [B,N*K]
+    eidx: np.ndarray     # [B,N*K] uint32  (u*K + k) | (n << 16)
+    colperm: np.ndarray  # [B,K] int32  sorted column position -> original cell type
+    nbig: np.ndarray     # [B] int32  leading elements with counts >= 6
+    nbig_min: int
+    y: np.ndarray        # [B,N,K]   counts after pseudocount, rows sorted by group (host-side reference copy)
     ntot: np.ndarray     # [B,N]
     xu: np.ndarray       # [B,Umax,D]
     grp: np.ndarray      # [B,N] int32
@@ -106,8 +113,24 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True) -> PackedProblem
     else:
         ycst = np.zeros_like(ys)
         lconst = prior_const + logp_const
+    if Umax * K > 65535 or N > 65535:
+        raise ValueError("packed element index needs Umax*K <= 65535 and N <= 65535")
+    # element list: column-major, columns sorted by decreasing minimum count (stable)
+    colmin = ys.min(axis=1)                                                   # [B,K]
+    colperm = np.argsort(-colmin, axis=1, kind="stable").astype(np.int32)     # [B,K]
+    nbig = (N * (colmin >= 6.0).sum(axis=1)).astype(np.int32)
+    bidx = np.arange(B)[:, None, None]
+    perm = colperm[:, :, None]                                                # [B,K,1]
+    rows = np.arange(N)[None, None, :]                                        # [1,1,N]
+    ey = ys[bidx, rows, perm].reshape(B, N * K)                               # [B,K,N] -> e = kk*N + n
+    eycst = ycst[bidx, rows, perm].reshape(B, N * K)
+    uk = grp[:, None, :].astype(np.int64) * K + perm                          # [B,K,N]
+    eidx = (uk | (rows.astype(np.int64) << 16)).astype(np.uint32).reshape(B, N * K)
     return PackedProblem(B=B, N=N, K=K, D=D, Umax=Umax, dtype=dtype,
-                         y=np.ascontiguousarray(ys, dtype), ycst=np.ascontiguousarray(ycst, dtype),
+                         ey=np.ascontiguousarray(ey, dtype), eycst=np.ascontiguousarray(eycst, dtype),
+                         eidx=np.ascontiguousarray(eidx), colperm=np.ascontiguousarray(colperm),
+                         nbig=nbig, nbig_min=int(nbig.min()),
+                         y=np.ascontiguousarray(ys, dtype),
                          ntot=np.ascontiguousarray(ntot, dtype), xu=np.ascontiguousarray(xu, dtype),
                          grp=np.ascontiguousarray(grp), rstart=np.ascontiguousarray(rstart), U=U, ref=ref,
                          lconst=np.ascontiguousarray(lconst, np.float64),

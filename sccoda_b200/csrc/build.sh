@@ -1,10 +1,22 @@
 #!/usr/bin/env bash
 # Builds libsccoda_b200.so (in-tree, sm_100a only).  Used by __graft_entry__.build().
+# The translation units are compiled in parallel and linked into one shared library.
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="${here}/../libsccoda_b200.so"
+obj="${here}/build"
+mkdir -p "${obj}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-"${NVCC}" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-    -Xcompiler -fPIC -shared ${SCCODA_NVCC_EXTRA:-} \
-    -o "${out}" "${here}/capi.cu" "${here}/kernels.cu" "${here}/summary.cu" "${here}/peaks.cu"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${SCCODA_NVCC_EXTRA:-})
+pids=()
+for src in capi kernels kernels_f32 kernels_f64 summary peaks; do
+    "${NVCC}" "${FLAGS[@]}" -c -o "${obj}/${src}.o" "${here}/${src}.cu" > "${obj}/${src}.log" 2>&1 &
+    pids+=($!)
+done
+fail=0
+for pid in "${pids[@]}"; do wait "${pid}" || fail=1; done
+cat "${obj}"/*.log
+if [ "${fail}" -ne 0 ]; then echo "nvcc failed" >&2; exit 1; fi
+"${NVCC}" -shared -o "${out}" "${obj}"/capi.o "${obj}"/kernels.o "${obj}"/kernels_f32.o "${obj}"/kernels_f64.o \
+    "${obj}"/summary.o "${obj}"/peaks.o
 echo "built ${out}"

@@ -44,10 +44,14 @@ int validate(const sccoda_problem* p) {
     if (!p) return fail(-1, "problem is NULL");
     if (p->B < 1 || p->C < 1) return fail(-2, "need B >= 1 and C >= 1 (got B=%d C=%d)", p->B, p->C);
     if (p->N < 1 || p->K < 2 || p->D < 1) return fail(-3, "need N >= 1, K >= 2, D >= 1 (got N=%d K=%d D=%d)", p->N, p->K, p->D);
+    if (p->D > 32) return fail(-3, "need D <= 32 covariates (got D=%d)", p->D);
     if (p->Umax < 1 || p->Umax > p->N) return fail(-4, "need 1 <= Umax <= N (got Umax=%d N=%d)", p->Umax, p->N);
     if (p->dtype != SCCODA_F32 && p->dtype != SCCODA_F64) return fail(-5, "dtype must be SCCODA_F32 or SCCODA_F64");
     if ((uint64_t)p->N * p->K * p->K >= 0x100000000ull) return fail(-6, "N*K*K must be < 2^32");
-    if (!p->y || !p->ycst || !p->ntot || !p->xu || !p->grp || !p->rstart || !p->U || !p->ref || !p->lconst)
+    if ((uint64_t)p->Umax * p->K > 65535ull || p->N > 65535) return fail(-6, "need Umax*K <= 65535 and N <= 65535 (packed element index)");
+    if (p->nbig_min < 0 || p->nbig_min > p->N * p->K) return fail(-6, "nbig_min out of range");
+    if (!p->ey || !p->eycst || !p->eidx || !p->colperm || !p->nbig || !p->ntot || !p->xu || !p->grp || !p->rstart ||
+        !p->U || !p->ref || !p->lconst)
         return fail(-7, "problem has a NULL array");
     return 0;
 }
@@ -59,7 +63,8 @@ void fill_dims(const sccoda_problem* p, sccoda::KArgs& a) {
     a.dm.magicK = magic_for(p->K);
     a.dm.magicK1 = magic_for(p->K - 1);  // 0 encodes a divisor of 1 (K == 2)
     a.B = p->B; a.C = p->C; a.Umax = p->Umax;
-    a.y = p->y; a.ycst = p->ycst; a.ntot = p->ntot; a.xu = p->xu;
+    a.ey = p->ey; a.eycst = p->eycst; a.eidx = p->eidx; a.colperm = p->colperm; a.nbig = p->nbig;
+    a.ntot = p->ntot; a.xu = p->xu;
     a.grp = p->grp; a.rstart = p->rstart; a.U = p->U; a.ref = p->ref; a.lconst = p->lconst;
 }
 
@@ -67,7 +72,7 @@ struct Plan {
     int W, cpc, grid, smem;
 };
 
-int make_plan(const sccoda_problem* p, const sccoda::KArgs& a, int kind, int W_req, Plan* out) {
+int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int kind, int W_req, Plan* out) {
     int dev = 0, max_smem = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
         cudaGetLastError();
@@ -90,6 +95,9 @@ int make_plan(const sccoda_problem* p, const sccoda::KArgs& a, int kind, int W_r
     int cpc = 128 / (32 * W);
     if (cpc < 1) cpc = 1;
     if (cpc > p->C) cpc = p->C;
+    // element list in shared memory: fp32 build only, and only while one chain group still fits
+    a.el_smem = (p->dtype == SCCODA_F32) ? 1 : 0;
+    if (a.el_smem && (int)sccoda::smem_bytes_for(a, kind, W, 1, p->dtype) > max_smem) a.el_smem = 0;
     while (cpc > 1 && (int)sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype) > max_smem) cpc -= 1;
     const size_t smem = sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype);
     if ((int)smem > max_smem)
@@ -201,10 +209,11 @@ int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, cons
     const size_t P = D + 2 * D * (K - 1) + K;
     struct Buf { void** dp; const void* hp; size_t bytes; };
     sccoda_problem pd = *ph;
-    void *d_y = nullptr, *d_ycst = nullptr, *d_ntot = nullptr, *d_xu = nullptr, *d_grp = nullptr, *d_rstart = nullptr,
-         *d_U = nullptr, *d_ref = nullptr, *d_lconst = nullptr, *d_init = nullptr, *d_draws = nullptr, *d_stats = nullptr,
-         *d_sum = nullptr;
-    Buf in[] = {{&d_y, ph->y, B * N * K * ts}, {&d_ycst, ph->ycst, B * N * K * ts}, {&d_ntot, ph->ntot, B * N * ts},
+    void *d_y = nullptr, *d_ycst = nullptr, *d_eidx = nullptr, *d_colperm = nullptr, *d_nbig = nullptr, *d_ntot = nullptr,
+         *d_xu = nullptr, *d_grp = nullptr, *d_rstart = nullptr, *d_U = nullptr, *d_ref = nullptr, *d_lconst = nullptr,
+         *d_init = nullptr, *d_draws = nullptr, *d_stats = nullptr, *d_sum = nullptr;
+    Buf in[] = {{&d_y, ph->ey, B * N * K * ts}, {&d_ycst, ph->eycst, B * N * K * ts}, {&d_eidx, ph->eidx, B * N * K * 4},
+                {&d_colperm, ph->colperm, B * K * 4}, {&d_nbig, ph->nbig, B * 4}, {&d_ntot, ph->ntot, B * N * ts},
                 {&d_xu, ph->xu, B * U * D * ts}, {&d_grp, ph->grp, B * N * 4}, {&d_rstart, ph->rstart, B * (U + 1) * 4},
                 {&d_U, ph->U, B * 4}, {&d_ref, ph->ref, B * 4}, {&d_lconst, ph->lconst, B * 8},
                 {&d_init, init, B * C * P * ts}};
@@ -227,7 +236,8 @@ int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, cons
         to_free.push_back(d_draws);
         if (cudaMalloc(&d_stats, stats_bytes) != cudaSuccess) { rc = fail(-42, "cudaMalloc(stats) failed"); break; }
         to_free.push_back(d_stats);
-        pd.y = d_y; pd.ycst = d_ycst; pd.ntot = d_ntot; pd.xu = d_xu; pd.grp = (const int32_t*)d_grp;
+        pd.ey = d_y; pd.eycst = d_ycst; pd.eidx = (const uint32_t*)d_eidx; pd.colperm = (const int32_t*)d_colperm;
+        pd.nbig = (const int32_t*)d_nbig; pd.ntot = d_ntot; pd.xu = d_xu; pd.grp = (const int32_t*)d_grp;
         pd.rstart = (const int32_t*)d_rstart; pd.U = (const int32_t*)d_U; pd.ref = (const int32_t*)d_ref;
         pd.lconst = (const double*)d_lconst;
         sccoda_sampler s2 = *smp;

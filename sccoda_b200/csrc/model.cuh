@@ -1,16 +1,23 @@
 // K1 — Dirichlet-multinomial spike-and-slab log-density and its analytic (digamma) gradient, evaluated
-// cooperatively by one "chain group" (W warps) entirely out of shared memory.
+// cooperatively by one "chain group" (W warps) out of shared memory.
 //
 // Replaces scCODAModel.target_log_prob_fn + TF autodiff:
 //   /root/reference/sccoda/model/scCODA_model.py:702-760 (density), :90-100 (inputs).
 //
-// Layout idea ("covariate groups"): rows n with identical covariate vectors x_n have identical
-// concentrations c_nk = exp(alpha_k + x_n . beta_k).  The host packer (sccoda_b200/_pack.py) sorts the rows
-// of a dataset by covariate group u = grp[n] (U groups, U <= N, U <= 2^D for binary designs) so that
-//   * exp / digamma(c) / lgamma(c) are evaluated U*K times instead of N*K,
-//   * row sums S_u = sum_k c_uk need no cross-lane reduction over the N*K element space,
-//   * only digamma(c_uk + y_nk) (and digamma(S_u + n_n)) remain per element / per row.
-// With continuous covariates U == N and the scheme degenerates to the plain evaluation.
+// Data layout (built by sccoda_b200/_pack.py, see include/sccoda_b200.h):
+//  * "covariate groups": rows n with identical covariate vectors x_n share their concentrations
+//    c_nk = exp(alpha_k + x_n . beta_k).  Rows are sorted by group u = grp[n] (U groups; U <= 2^D for binary
+//    designs, U == N for continuous covariates), so exp / digamma(c) are evaluated U*K times, not N*K, and the
+//    row sums S_u need no reduction over the N*K element space.
+//  * "element list": the N*K counts are stored column-major with the columns (cell types) sorted by decreasing
+//    minimum count.  Element e = kk*N + n carries y_e, a host constant ycst_e and a packed index
+//    (u*K + k) | (n << 16).  The first `nbig` elements belong to columns whose counts are all >= 6: for them
+//    digamma(c + y) needs no recurrence shift (2 MUFU + 6 FMA, branch-free, no warp vote); the few remaining
+//    elements take the general digamma.  (y, index) pairs are staged once into shared memory as 8-byte
+//    records (one LDS.64 per element), (c, digamma(c)) pairs likewise.
+//
+// All shared-memory arrays are addressed as 32-bit byte offsets from the dynamic shared-memory base, so that
+// every access is an LDS/STS with a 32-bit address (no generic-pointer arithmetic, fewer registers).
 //
 // State vector theta (flat, order of scCODA_model.py:692-693, 763-768):
 //   [ sigma_d (D) | b_offset (D,K-1) | ind_raw (D,K-1) | alpha (K) ]
@@ -21,52 +28,75 @@
 
 namespace sccoda {
 
+extern __shared__ __align__(16) unsigned char sccoda_smem[];
+
+// typed view of a shared-memory array given its byte offset
+template <typename V>
+__device__ __forceinline__ V* sp(uint32_t off) {
+    return reinterpret_cast<V*>(sccoda_smem + off);
+}
+
 struct Dims {
     int N, K, D, P;
     int K1;    // K-1
     int DK1;   // D*(K-1)
     int NK;    // N*K
-    uint32_t magicK, magicK1;  // ceil(2^32/K), ceil(2^32/(K-1)) for exact small-range division
+    uint32_t magicK, magicK1;  // ceil(2^32/K), ceil(2^32/(K-1)); 0 encodes a divisor of 1
 };
 
-// magic == 0 encodes a divisor of 1
 __device__ __forceinline__ int fast_div(int e, uint32_t magic) {
     return magic ? (int)__umulhi((uint32_t)e, magic) : e;
 }
 
-// One dataset resident in shared memory (shared by all chain groups of the CTA).
+// One element of the list: count and packed index (u*K + k) | (n << 16); 8 bytes in the fp32 build (LDS.64).
 template <typename T>
-struct DataTile {
-    const T* y;         // [N,K] counts after pseudocount, rows sorted by group
-    const T* ycst;      // [N,K] host constant for lgamma_shift (fp32: r(y) or lgamma(y); fp64: 0)
-    const T* ntot;      // [N]
-    const T* xu;        // [U,D] unique covariate rows
-    const int* grp;     // [N] group of row n (non-decreasing)
-    const int* rstart;  // [U+1] first row of each group
-    int U;
-    int ref;
-    double lconst;  // all theta-independent terms of the log-density (host, fp64)
+struct alignas(2 * sizeof(T)) Elem {
+    T y;
+    uint32_t idx;
+};
+// concentration and its digamma, read together
+template <typename T>
+struct alignas(2 * sizeof(T)) CPsi {
+    T c;
+    T psi;
 };
 
-// Scratch of one chain group.
+// One dataset (shared by all chain groups of the CTA): shared-memory offsets + global pointers.
 template <typename T>
+struct DataTile {
+    uint32_t ntot;         // smem T[N]
+    uint32_t xu;           // smem T[U,D] unique covariate rows
+    uint32_t grp;          // smem int[N] group of row n (non-decreasing)
+    uint32_t rstart;       // smem int[U+1] first row of each group
+    uint32_t colperm;      // smem int[K] sorted column position -> original cell type
+    uint32_t el;           // smem Elem<T>[NK] element list (only when el_smem)
+    int el_smem;
+    const T* ey;           // global [NK]
+    const uint32_t* eidx;  // global [NK]
+    const T* eycst;        // global [NK] host constants of the value pass
+    int U, ref;
+    int nbig;              // elements [0, nbig) have counts >= 6
+    double lconst;         // all theta-independent terms of the log-density (host, fp64)
+};
+
+// Scratch of one chain group (shared-memory byte offsets).
 struct ChainScratch {
-    T* c;        // [U,K] concentrations
-    T* psic;     // [U,K] digamma(c)
-    T* rowterm;  // [N]   digamma(S_u + n_n) - digamma(S_u)
-    T* G;        // [N,K] d logp / d log c_nk
-    T* Gu;       // [U,K] per-group column sums of G
-    T* beta;     // [D,K] (reference column stays 0)
-    T* ind;      // [D,K-1]
-    T* gk;       // [(1+D),K]: row 0 = sum_n G_nk, row 1+d = sum_n x_nd G_nk
+    uint32_t cp;       // CPsi<T>[U,K] concentrations c_uk and digamma(c_uk)
+    uint32_t rowterm;  // T[N]   digamma(S_u + n_n) - digamma(S_u)
+    uint32_t G;        // T[NK]  d logp / d log c, element-list order
+    uint32_t Gu;       // T[U,K] per-group column sums of G
+    uint32_t beta;     // T[D,K] (reference column stays 0)
+    uint32_t ind;      // T[D,K-1]
+    uint32_t gk;       // T[(1+D),K]: row 0 = sum_n G_nk, row 1+d = sum_n x_nd G_nk
+    uint32_t vec;      // T[nvec, vs] state vectors of the sampler
 };
 
 // Thread-group abstraction: W warps cooperating on one chain.  W == 1 needs no block barrier at all.
 template <int W>
 struct Group {
-    int tid;      // thread index inside the group
-    int gid;      // group slot inside the CTA (named barrier id = gid + 1)
-    double* red;  // [2*W] reduction scratch (W > 1)
+    int tid;       // thread index inside the group
+    int gid;       // group slot inside the CTA (named barrier id = gid + 1)
+    uint32_t red;  // smem double[2*W] reduction scratch (W > 1)
     static constexpr int SIZE = 32 * W;
 
     __device__ __forceinline__ void sync() const {
@@ -81,7 +111,7 @@ struct Group {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (W > 1) {
-            V* r = reinterpret_cast<V*>(red);
+            V* r = sp<V>(red);
             sync();  // previous consumers of red are done
             if ((tid & 31) == 0) r[tid >> 5] = v;
             sync();
@@ -93,153 +123,235 @@ struct Group {
     }
 };
 
-// Evaluate gradient (always) and value (WITH_LOGP) at theta.  theta/grad live in shared memory.
-// On return grad[] is complete and visible to the whole group (trailing sync included).
-// The value is returned to every thread (group-reduced); accumulation is fp64 in both builds.
-template <typename T, bool WITH_LOGP, int W>
-__device__ __forceinline__ double dm_eval(const Dims& dm, const DataTile<T>& dt, const ChainScratch<T>& cs,
-                                          const T* __restrict__ theta, T* __restrict__ grad, const Group<W>& g) {
+// Gradient of the log-density at theta (theta/grad: shared-memory offsets of T[P]).  On return grad[] is
+// complete and visible to the whole group (trailing sync included); the scratch keeps c_uk for dm_value.
+template <typename T, int W>
+__device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                        uint32_t theta_off, uint32_t grad_off, const Group<W>& g) {
     const int tid = g.tid;
     constexpr int TS = Group<W>::SIZE;
-    const int K = dm.K, D = dm.D, K1 = dm.K1, DK1 = dm.DK1, U = dt.U, ref = dt.ref;
-    const T* sigma = theta;
-    const T* boff = theta + D;
-    const T* iraw = theta + D + DK1;
-    const T* alpha = theta + D + 2 * DK1;
-    double lp = 0.0;
+    const int K = dm.K, D = dm.D, K1 = dm.K1, DK1 = dm.DK1, N = dm.N, U = dt.U, ref = dt.ref;
+    const T* sigma = sp<T>(theta_off);
+    const T* boff = sigma + D;
+    const T* iraw = boff + DK1;
+    const T* alpha = iraw + DK1;
+    T* grad = sp<T>(grad_off);
+    CPsi<T>* cp = sp<CPsi<T>>(cs.cp);
+    T* rowterm = sp<T>(cs.rowterm);
+    T* G = sp<T>(cs.G);
+    T* Gu = sp<T>(cs.Gu);
+    T* beta = sp<T>(cs.beta);
+    T* ind = sp<T>(cs.ind);
+    T* gk = sp<T>(cs.gk);
+    const T* xu = sp<T>(dt.xu);
+    const T* ntot = sp<T>(dt.ntot);
+    const int* grp = sp<int>(dt.grp);
+    const int* rstart = sp<int>(dt.rstart);
+    const int* colperm = sp<int>(dt.colperm);
 
     // ---- phase 1: spike-and-slab effects  beta = sigmoid(50 ind_raw) * sigma_d * b_offset   (:724-734)
+#pragma unroll 1
     for (int i = tid; i < DK1; i += TS) {
         const int d = fast_div(i, dm.magicK1);
         const int j = i - d * K1;
         const int k = j + (j >= ref);
-        const T bo = boff[i], ir = iraw[i];
-        const T ind = sigmoid_stable(T(50) * ir);
-        cs.ind[i] = ind;
-        cs.beta[d * K + k] = ind * sigma[d] * bo;
-        if (WITH_LOGP) lp += (double)(T(-0.5) * (bo * bo + ir * ir));  // Normal(0,1) x2   (:709-722)
-    }
-    if (WITH_LOGP) {
-        for (int k = tid; k < K; k += TS) lp += (double)(alpha[k] * alpha[k] * T(-0.02));  // Normal(0,5) (:736-741)
-        for (int d = tid; d < D; d += TS) {                                                // HalfCauchy(0,1) (:703-707)
-            const T s = sigma[d];
-            if (s >= T(0)) lp -= log1p((double)s * (double)s);
-        }
+        const T id = sigmoid_stable(T(50) * iraw[i]);
+        ind[i] = id;
+        beta[d * K + k] = id * sigma[d] * boff[i];
     }
     g.sync();
 
     // ---- phase 2: per covariate group  c_uk = exp(alpha_k + x_u . beta_k), digamma(c_uk)          (:743)
+#pragma unroll 1
     for (int e = tid; e < U * K; e += TS) {
         const int u = fast_div(e, dm.magicK);
         const int k = e - u * K;
         T eta = alpha[k];
-        for (int d = 0; d < D; ++d) eta = fma(dt.xu[u * D + d], cs.beta[d * K + k], eta);
-        const T c = exp_acc(eta);
-        cs.c[e] = c;
-        cs.psic[e] = digamma_pos(c);
-        if (WITH_LOGP) lp -= (double)((T)(dt.rstart[u + 1] - dt.rstart[u]) * lgamma_pos(c));
+#pragma unroll 2
+        for (int d = 0; d < D; ++d) eta = fma(xu[u * D + d], beta[d * K + k], eta);
+        CPsi<T> v;
+        v.c = exp_acc(eta);
+        v.psi = digamma_pos(v.c);
+        cp[e] = v;
     }
     g.sync();
 
     // ---- phase 3: rows  S_u, digamma(S_u + n_n) - digamma(S_u)
-    for (int n = tid; n < dm.N; n += TS) {
-        const int u = dt.grp[n];
-        const T* cu = cs.c + u * K;
-        T S = T(0);
-        for (int k = 0; k < K; ++k) S += cu[k];
-        const T nt = dt.ntot[n];
-        cs.rowterm[n] = digamma_pos(S + nt) - digamma_pos(S);
-        // the two O(n ln n)-sized terms are taken in fp64 (2 per row per value evaluation)
-        if (WITH_LOGP) lp += lgamma((double)S) - lgamma((double)S + (double)nt);
+#pragma unroll 1
+    for (int n = tid; n < N; n += TS) {
+        const CPsi<T>* cu = cp + grp[n] * K;
+        T S0 = T(0), S1 = T(0);
+        int k = 0;
+#pragma unroll 2
+        for (; k + 1 < K; k += 2) {
+            S0 += cu[k].c;
+            S1 += cu[k + 1].c;
+        }
+        if (k < K) S0 += cu[k].c;
+        const T S = S0 + S1;
+        rowterm[n] = digamma_pos(S + ntot[n]) - digamma_pos(S);
     }
     g.sync();
 
-    // ---- phase 4: elements  G_nk = c (digamma(c+y) - digamma(c) - rowterm_n)
-    {
-        const int iters = (dm.NK + TS - 1) / TS;
-        for (int it = 0; it < iters; ++it) {
-            const int e = tid + it * TS;
-            const bool valid = e < dm.NK;
-            const int ee = valid ? e : 0;
-            const int n = fast_div(ee, dm.magicK);
-            const int k = ee - n * K;
-            const int uk = dt.grp[n] * K + k;
-            const T yv = dt.y[ee];
-            const T c = cs.c[uk];
-            const T z = c + yv;
-            // warp-uniform choice: when every lane's count is >= 6 no recurrence shift is needed
-            const bool big = __all_sync(0xffffffffu, (yv >= T(6)) || !valid);
-            const T psi = big ? digamma_big(z) : digamma_pos(z);
-            if (valid) {
-                cs.G[e] = c * (psi - cs.psic[uk] - cs.rowterm[n]);
-                if (WITH_LOGP) lp += (double)lgamma_shift(c, yv, sizeof(T) == 4 ? dt.ycst[e] : T(0));
-            }
+    // ---- phase 4: elements  G = c (digamma(c+y) - digamma(c) - rowterm_n)
+    if (dt.el_smem) {
+        const Elem<T>* el = sp<Elem<T>>(dt.el);
+        // 4a: counts >= 6, no recurrence shift needed
+#pragma unroll 4
+        for (int e = tid; e < dt.nbig; e += TS) {
+            const Elem<T> v = el[e];
+            const CPsi<T> q = cp[v.idx & 0xffffu];
+            G[e] = q.c * (digamma_big(q.c + v.y) - q.psi - rowterm[v.idx >> 16]);
+        }
+        // 4b: columns that contain small counts: general digamma
+#pragma unroll 1
+        for (int e = dt.nbig + tid; e < dm.NK; e += TS) {
+            const Elem<T> v = el[e];
+            const CPsi<T> q = cp[v.idx & 0xffffu];
+            G[e] = q.c * (digamma_pos(q.c + v.y) - q.psi - rowterm[v.idx >> 16]);
+        }
+    } else {
+        // element list streamed from global memory (fp64 parity build, or tiles too large for shared memory)
+#pragma unroll 1
+        for (int e = tid; e < dm.NK; e += TS) {
+            const uint32_t ix = dt.eidx[e];
+            const CPsi<T> q = cp[ix & 0xffffu];
+            G[e] = q.c * (digamma_pos(q.c + dt.ey[e]) - q.psi - rowterm[ix >> 16]);
         }
     }
     g.sync();
 
-    // ---- phase 5: per-group column sums  Gu_uk = sum_{n in u} G_nk
+    // ---- phase 5: per-group column sums  Gu_uk = sum_{n in u} G_nk   (element e = kk*N + n)
+#pragma unroll 1
     for (int e = tid; e < U * K; e += TS) {
         const int u = fast_div(e, dm.magicK);
-        const int k = e - u * K;
-        T s = T(0);
-        for (int n = dt.rstart[u]; n < dt.rstart[u + 1]; ++n) s += cs.G[n * K + k];
-        cs.Gu[e] = s;
+        const int kk = e - u * K;
+        const T* col = G + kk * N;
+        const int n1 = rstart[u + 1];
+        T s0 = T(0), s1 = T(0);
+        int n = rstart[u];
+#pragma unroll 2
+        for (; n + 1 < n1; n += 2) {
+            s0 += col[n];
+            s1 += col[n + 1];
+        }
+        if (n < n1) s0 += col[n];
+        Gu[u * K + colperm[kk]] = s0 + s1;
     }
     g.sync();
 
     // ---- phase 6: gk[0,k] = sum_n G_nk ; gk[1+d,k] = sum_n x_nd G_nk
+#pragma unroll 1
     for (int e = tid; e < (D + 1) * K; e += TS) {
         const int r = fast_div(e, dm.magicK);
         const int k = e - r * K;
         T s = T(0);
         if (r == 0) {
-            for (int u = 0; u < U; ++u) s += cs.Gu[u * K + k];
+#pragma unroll 2
+            for (int u = 0; u < U; ++u) s += Gu[u * K + k];
         } else {
-            for (int u = 0; u < U; ++u) s = fma(dt.xu[u * D + (r - 1)], cs.Gu[u * K + k], s);
+#pragma unroll 2
+            for (int u = 0; u < U; ++u) s = fma(xu[u * D + (r - 1)], Gu[u * K + k], s);
         }
-        cs.gk[e] = s;
+        gk[e] = s;
     }
     g.sync();
 
     // ---- phase 7: chain rule back to the unconstrained parameters
+    // 7a: d/d sigma_d (likelihood part) = sum_k g_dk ind_dk b_offset_dk — one group reduction per covariate,
+    //     kept by thread d (D <= 32 is checked on the host), which also owns parameter sigma_d below.
+    T my_sg = T(0);
+#pragma unroll 1
+    for (int d = 0; d < D; ++d) {
+        T part = T(0);
+#pragma unroll 1
+        for (int j = tid; j < K1; j += TS) {
+            const int k = j + (j >= ref);
+            part = fma(gk[(1 + d) * K + k] * ind[d * K1 + j], boff[d * K1 + j], part);
+        }
+        part = g.sum(part);
+        if (tid == d) my_sg = part;
+    }
+#pragma unroll 1
     for (int i = tid; i < dm.P; i += TS) {
         T gr;
         if (i < D) {
-            const int d = i;
-            T acc = T(0);
-            for (int j = 0; j < K1; ++j) {
-                const int k = j + (j >= ref);
-                acc = fma(cs.gk[(1 + d) * K + k] * cs.ind[d * K1 + j], boff[d * K1 + j], acc);
-            }
-            const T s = sigma[d];
+            const T s = sigma[i];
             // HalfCauchy on the unconstrained sigma_d: zero prior gradient for sigma_d < 0 [TFP]
-            gr = acc - (s >= T(0) ? T(2) * s / (T(1) + s * s) : T(0));
+            gr = my_sg - (s >= T(0) ? T(2) * s / (T(1) + s * s) : T(0));
         } else if (i < D + 2 * DK1) {
             const bool is_off = i < D + DK1;
             const int ii = is_off ? i - D : i - D - DK1;
             const int d = fast_div(ii, dm.magicK1);
             const int j = ii - d * K1;
             const int k = j + (j >= ref);
-            const T gg = cs.gk[(1 + d) * K + k];
-            const T ind = cs.ind[ii];
+            const T gg = gk[(1 + d) * K + k];
+            const T id = ind[ii];
             const T s = sigma[d];
-            if (is_off) gr = gg * ind * s - boff[ii];
-            else gr = gg * s * boff[ii] * T(50) * ind * (T(1) - ind) - iraw[ii];
+            if (is_off) gr = gg * id * s - boff[ii];
+            else gr = gg * s * boff[ii] * T(50) * id * (T(1) - id) - iraw[ii];
         } else {
             const int k = i - D - 2 * DK1;
-            gr = cs.gk[k] - alpha[k] * T(0.04);
+            gr = gk[k] - alpha[k] * T(0.04);
         }
         grad[i] = gr;
     }
     g.sync();
+}
 
-    if (WITH_LOGP) {
-        lp = g.sum(lp) + dt.lconst;
-        // HalfCauchy support: -inf as soon as one sigma_d < 0 [TFP]; every thread scans the D values (uniform)
-        for (int d = 0; d < D; ++d)
-            if (sigma[d] < T(0)) lp = -CUDART_INF;
+// Value of the log-density at theta.  Must follow dm_grad at the same theta (uses the c_uk it left in the
+// scratch).  Terms are evaluated in T, accumulated in fp64; the two O(n ln n)-sized row terms are taken in
+// fp64.  Every thread of the group receives the result.
+template <typename T, int W>
+__device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                        uint32_t theta_off, const Group<W>& g) {
+    const int tid = g.tid;
+    constexpr int TS = Group<W>::SIZE;
+    const int K = dm.K, D = dm.D, DK1 = dm.DK1, U = dt.U;
+    const T* sigma = sp<T>(theta_off);
+    const T* boff = sigma + D;
+    const T* iraw = boff + DK1;
+    const T* alpha = iraw + DK1;
+    const CPsi<T>* cp = sp<CPsi<T>>(cs.cp);
+    const int* rstart = sp<int>(dt.rstart);
+    const int* grp = sp<int>(dt.grp);
+    const T* ntot = sp<T>(dt.ntot);
+    double lp = 0.0;
+#pragma unroll 1
+    for (int i = tid; i < DK1; i += TS) {                                             // Normal(0,1) x2 (:709-722)
+        const T bo = boff[i], ir = iraw[i];
+        lp += (double)(T(-0.5) * (bo * bo + ir * ir));
     }
+#pragma unroll 1
+    for (int k = tid; k < K; k += TS) lp += (double)(alpha[k] * alpha[k] * T(-0.02));  // Normal(0,5)   (:736-741)
+#pragma unroll 1
+    for (int d = tid; d < D; d += TS) {                                                // HalfCauchy(0,1) (:703-707)
+        const double s = (double)sigma[d];
+        if (s >= 0.0) lp -= log1p(s * s);
+    }
+    // DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c)                               (:746-751)
+#pragma unroll 1
+    for (int e = tid; e < U * K; e += TS) {
+        const int u = fast_div(e, dm.magicK);
+        lp -= (double)((T)(rstart[u + 1] - rstart[u]) * lgamma_pos(cp[e].c));
+    }
+#pragma unroll 1
+    for (int n = tid; n < dm.N; n += TS) {
+        const CPsi<T>* cu = cp + grp[n] * K;
+        T S = T(0);
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) S += cu[k].c;
+        lp += lgamma_f64((double)S) - lgamma_f64((double)S + (double)ntot[n]);
+    }
+#pragma unroll 1
+    for (int e = tid; e < dm.NK; e += TS) {
+        const uint32_t ix = dt.eidx[e];
+        lp += (double)lgamma_shift(cp[ix & 0xffffu].c, dt.ey[e], sizeof(T) == 4 ? dt.eycst[e] : T(0));
+    }
+    lp = g.sum(lp) + dt.lconst;
+    // HalfCauchy support: -inf as soon as one sigma_d < 0 [TFP]; every thread scans the D values (uniform)
+    for (int d = 0; d < D; ++d)
+        if (sigma[d] < T(0)) lp = -CUDART_INF;
     return lp;
 }
 

@@ -126,9 +126,28 @@ __device__ __forceinline__ double digamma_pos(double x) {
     return acc + log(x) - 0.5 * w - ser;
 }
 __device__ __forceinline__ double digamma_big(double z) { return digamma_pos(z); }
-__device__ __forceinline__ double lgamma_pos(double x) { return lgamma(x); }
+
+// lgamma(x), x > 0, fp64: recurrence up to x >= 10, then Stirling with 7 correction terms (|err| ~ 1e-15 rel).
+// Kept out of line: it is called a handful of times per value evaluation and libdevice's lgamma is ~3 KB of code.
+static __device__ __noinline__ double lgamma_f64(double x) {
+    if (!(x > 0.0)) return (x == 0.0) ? CUDART_INF : CUDART_NAN;
+    if (isinf(x)) return x;
+    double prod = 1.0;
+    while (x < 10.0) {
+        prod *= x;
+        x += 1.0;
+    }
+    const double w = 1.0 / x, w2 = w * w;
+    const double ser =
+        w * (1.0 / 12.0 -
+             w2 * (1.0 / 360.0 -
+                   w2 * (1.0 / 1260.0 -
+                         w2 * (1.0 / 1680.0 - w2 * (1.0 / 1188.0 - w2 * (691.0 / 360360.0 - w2 * (1.0 / 156.0)))))));
+    return (x - 0.5) * log(x) - x + 0.91893853320467274178 + ser - log(prod);
+}
+__device__ __forceinline__ double lgamma_pos(double x) { return lgamma_f64(x); }
 // fp64: ycst = 0 and the host constant carries nothing extra — plain lgamma(c+y).
-__device__ __forceinline__ double lgamma_shift(double c, double y, double ycst) { return lgamma(c + y) - ycst; }
+__device__ __forceinline__ double lgamma_shift(double c, double y, double ycst) { return lgamma_f64(c + y) - ycst; }
 __device__ __forceinline__ double exp_acc(double x) { return exp(x); }
 __device__ __forceinline__ double sigmoid_stable(double s) {
     const double e = exp(-fabs(s));

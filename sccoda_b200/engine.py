@@ -56,14 +56,17 @@ class DeviceProblem:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.tdtype = torch.float32 if packed.dtype == np.float32 else torch.float64
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=False)
-        self.y, self.ycst, self.ntot, self.xu = up(packed.y), up(packed.ycst), up(packed.ntot), up(packed.xu)
+        self.ey, self.eycst, self.eidx = up(packed.ey), up(packed.eycst), up(packed.eidx.view(np.int32))
+        self.colperm, self.nbig = up(packed.colperm), up(packed.nbig)
+        self.ntot, self.xu = up(packed.ntot), up(packed.xu)
         self.grp, self.rstart, self.U, self.ref = up(packed.grp), up(packed.rstart), up(packed.U), up(packed.ref)
         self.lconst = up(packed.lconst)
         self.B, self.N, self.K, self.D, self.P = packed.B, packed.N, packed.K, packed.D, packed.P
         self.c_problem = nat.Problem(
             B=self.B, C=self.C, N=self.N, K=self.K, D=self.D, Umax=packed.Umax,
-            dtype=nat.F32 if packed.dtype == np.float32 else nat.F64, reserved=0,
-            y=_ptr(self.y), ycst=_ptr(self.ycst), ntot=_ptr(self.ntot), xu=_ptr(self.xu), grp=_ptr(self.grp),
+            dtype=nat.F32 if packed.dtype == np.float32 else nat.F64, nbig_min=packed.nbig_min,
+            ey=_ptr(self.ey), eycst=_ptr(self.eycst), eidx=_ptr(self.eidx), colperm=_ptr(self.colperm),
+            nbig=_ptr(self.nbig), ntot=_ptr(self.ntot), xu=_ptr(self.xu), grp=_ptr(self.grp),
             rstart=_ptr(self.rstart), U=_ptr(self.U), ref=_ptr(self.ref), lconst=_ptr(self.lconst))
 
     @classmethod
@@ -179,8 +182,10 @@ def sample_host(packed: PackedProblem, chains: int, init: np.ndarray, smp: nat.S
     init = np.ascontiguousarray(init, dtype=dt)
     assert init.shape == (B, C, P)
     prob = nat.Problem(B=B, C=C, N=packed.N, K=packed.K, D=packed.D, Umax=packed.Umax,
-                       dtype=nat.F32 if dt == np.float32 else nat.F64, reserved=0,
-                       y=packed.y.ctypes.data, ycst=packed.ycst.ctypes.data, ntot=packed.ntot.ctypes.data,
+                       dtype=nat.F32 if dt == np.float32 else nat.F64, nbig_min=packed.nbig_min,
+                       ey=packed.ey.ctypes.data, eycst=packed.eycst.ctypes.data, eidx=packed.eidx.ctypes.data,
+                       colperm=packed.colperm.ctypes.data, nbig=packed.nbig.ctypes.data,
+                       ntot=packed.ntot.ctypes.data,
                        xu=packed.xu.ctypes.data, grp=packed.grp.ctypes.data, rstart=packed.rstart.ctypes.data,
                        U=packed.U.ctypes.data, ref=packed.ref.ctypes.data, lconst=packed.lconst.ctypes.data)
     draws = np.empty((B, C, S, P), dtype=dt) if want_draws else None

@@ -41,8 +41,10 @@ def test_header_constants_match_binding():
 
 
 def _problem(pk, C):
-    return nat.Problem(B=pk.B, C=C, N=pk.N, K=pk.K, D=pk.D, Umax=pk.Umax, dtype=nat.F32, reserved=0,
-                       y=pk.y.ctypes.data, ycst=pk.ycst.ctypes.data, ntot=pk.ntot.ctypes.data, xu=pk.xu.ctypes.data,
+    return nat.Problem(B=pk.B, C=C, N=pk.N, K=pk.K, D=pk.D, Umax=pk.Umax, dtype=nat.F32, nbig_min=pk.nbig_min,
+                       ey=pk.ey.ctypes.data, eycst=pk.eycst.ctypes.data, eidx=pk.eidx.ctypes.data,
+                       colperm=pk.colperm.ctypes.data, nbig=pk.nbig.ctypes.data,
+                       ntot=pk.ntot.ctypes.data, xu=pk.xu.ctypes.data,
                        grp=pk.grp.ctypes.data, rstart=pk.rstart.ctypes.data, U=pk.U.ctypes.data,
                        ref=pk.ref.ctypes.data, lconst=pk.lconst.ctypes.data)
 
@@ -100,7 +102,7 @@ def test_problem_validation():
     p = _problem(pk, 0)
     assert _plan(p, _sampler())[0] == -2
     p = _problem(pk, 4)
-    p.y = None
+    p.ey = None
     assert _plan(p, _sampler())[0] == -7
 
 

@@ -40,12 +40,32 @@ def test_fp32_constants():
     y[0, 0] = 0
     y[1, 1] = 3
     pk = pack(x, y, 4, dtype=np.float32)
-    ys = pk.y[0].astype(np.float64)
+    ys = pk.ey[0].astype(np.float64)
     big = ys >= 6
     stir = (ys - 0.5) * np.log(ys) - ys + 0.5 * math.log(2 * math.pi)
-    assert np.allclose(pk.ycst[0][big], (gammaln(ys) - stir)[big], atol=1e-7)
-    assert np.allclose(pk.ycst[0][~big], gammaln(ys)[~big], rtol=1e-6)
+    assert np.allclose(pk.eycst[0][big], (gammaln(ys) - stir)[big], atol=1e-7)
+    assert np.allclose(pk.eycst[0][~big], gammaln(ys)[~big], rtol=1e-6)
     assert (~big).sum() >= 2
+
+
+def test_element_list_layout():
+    """Column-major, columns sorted by decreasing minimum count; packed index (u*K + k) | (n << 16)."""
+    x, y = synthetic_dataset(4, N=8, K=6)
+    y[3, 2] = 0          # column 2 becomes a small-count column
+    y[:, 5] = 2          # column 5 too
+    pk = pack(x, y, 0, dtype=np.float64)
+    N, K = 8, 6
+    ys, grp = pk.y[0], pk.grp[0]
+    colmin = ys.min(axis=0)
+    assert np.all(np.diff(colmin[pk.colperm[0]]) <= 0)
+    assert pk.nbig[0] == N * (colmin >= 6).sum() == pk.nbig_min
+    assert set(pk.colperm[0][pk.nbig[0] // N:]) >= {2, 5}
+    for e in range(N * K):
+        kk, n = divmod(e, N)
+        k = pk.colperm[0][kk]
+        assert pk.ey[0][e] == ys[n, k]
+        assert pk.eidx[0][e] == (grp[n] * K + k) | (n << 16)
+    assert np.all(pk.ey[0][:pk.nbig[0]] >= 6)
 
 
 def test_continuous_covariates_have_one_group_per_row():

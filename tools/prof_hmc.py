@@ -1,0 +1,39 @@
+"""Short single-launch run of the sampler kernel at the benchmark shape, for ncu captures (tools, not product)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from sccoda_b200 import _native as nat
+from sccoda_b200 import scheduler as sch
+from sccoda_b200._pack import pack
+from sccoda_b200.engine import DeviceProblem
+from sccoda_b200.util.data_generation import generate_sweep
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--datasets", type=int, default=1024)
+ap.add_argument("--chains", type=int, default=4)
+ap.add_argument("--K", type=int, default=20)
+ap.add_argument("--n-per-group", type=int, default=10)
+ap.add_argument("--results", type=int, default=100)
+ap.add_argument("--burnin", type=int, default=20)
+ap.add_argument("--method", type=int, default=0)
+ap.add_argument("--W", type=int, default=0)
+ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--step-size", type=float, default=0.02)
+a = ap.parse_args()
+
+x, y, _ = generate_sweep(a.datasets, K=a.K, n_per_group=a.n_per_group)
+pk = pack(x, y, a.K - 1, dtype=np.float32)
+init = sch.initial_states(a.datasets, a.chains, 1, a.K, seed=1).astype(np.float32)
+prob = DeviceProblem(pk, chains=a.chains)
+smp = prob.make_sampler(a.method, a.results, a.burnin, step_size=a.step_size, seed=3, warps_per_chain=a.W)
+for _ in range(a.reps):
+    out = prob.sample(init, smp)
+ge = a.datasets * a.chains * (a.results + a.burnin) * 10
+print(f"W={out.warps_per_chain} cpc={out.chains_per_cta} grid={out.grid} smem={out.smem_bytes} ms={out.kernel_ms:.3f} "
+      f"grad-evals/s={ge / out.kernel_ms * 1e3:.4e} acc={out.stat('is_accepted').mean().item():.3f}")
