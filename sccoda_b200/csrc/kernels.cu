@@ -7,7 +7,7 @@ namespace sccoda {
 
 int nvec_for(int kind, int max_depth) {
     if (kind == KIND_LOGP) return 2;
-    if (kind == KIND_HMC) return 5;
+    if (kind == KIND_HMC) return 6;
     return 15 + 2 * (max_depth + 1);
 }
 

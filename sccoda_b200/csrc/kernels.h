@@ -68,7 +68,7 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
     p.cp = o; o += rnd16(UK * 2 * ts);
     p.rowterm = o; o += rnd16((size_t)N * ts);
     p.G = o; o += rnd16(NK * ts);
-    p.Gu = o; o += rnd16(UK * ts);
+    p.Gu = o; o += rnd16((size_t)Umax * ts);
     p.beta = o; o += rnd16((size_t)D * K * ts);
     p.ind = o; o += rnd16((size_t)D * (K - 1) * ts + ts);
     p.gk = o; o += rnd16((size_t)(D + 1) * K * ts);

@@ -115,7 +115,7 @@ __global__ void SCCODA_BOUNDS(W) logp_grad_kernel(const __grid_constant__ KArgs 
     const T* theta_in = static_cast<const T*>(a.init) + chain * P;
     for (int i = g.tid; i < P; i += TS) sp<T>(th)[i] = theta_in[i];
     g.sync();
-    dm_grad<T, W>(a.dm, dt, cs, th, gr, g);
+    dm_grad<T, W>(a.dm, dt, cs, th, g, StoreGrad<T>{sp<T>(gr)});
     const double lp = dm_value<T, W>(a.dm, dt, cs, th, g);
     T* grad_out = static_cast<T*>(a.draws) + chain * P;
     for (int i = g.tid; i < P; i += TS) grad_out[i] = sp<T>(gr)[i];
@@ -201,27 +201,48 @@ __device__ __forceinline__ void store_chain_state(const KArgs& a, size_t chain, 
 // ------------------------------------------------------------------------------------------------
 // K2: HMC  ([TFP] HamiltonianMonteCarlo.one_step + MetropolisHastings + step-size adaptation)
 // ------------------------------------------------------------------------------------------------
+// Leapfrog epilogue fused into the gradient's back-propagation: for every parameter i (called once, by its owner)
+//   g_work[i] = grad;  p[i] += f * grad;  if (advance) theta_next[i] = theta_cur[i] + eps * p[i]
+template <typename T>
+struct LeapfrogEpi {
+    T* gw;
+    T* mom;
+    const T* cur;
+    T* nxt;
+    T f, eps;
+    bool kick, advance;
+    __device__ __forceinline__ void operator()(int i, T gr) const {
+        gw[i] = gr;
+        if (kick) {
+            const T m = fma(f, gr, mom[i]);
+            mom[i] = m;
+            if (advance) nxt[i] = fma(eps, m, cur[i]);
+        }
+    }
+};
+
 template <typename T, int W>
 __global__ void SCCODA_BOUNDS(W) hmc_kernel(const __grid_constant__ KArgs a) {
     DataTile<T> dt;
     ChainScratch cs;
     Group<W> g;
     int b, c;
-    if (!prologue<T, W>(a, 5, dt, cs, g, b, c)) return;
+    if (!prologue<T, W>(a, 6, dt, cs, g, b, c)) return;
     constexpr int TS = 32 * W;
     const int P = a.dm.P, tid = g.tid;
     const uint32_t vs = vec_stride_bytes<T>(P);
-    // state vectors (shared-memory byte offsets); "current" and "work" swap roles on acceptance
+    // state vectors (shared-memory byte offsets); the roles rotate on acceptance
     uint32_t o_thc = cs.vec;            // current state
     uint32_t o_gc = cs.vec + vs;        // its gradient
-    uint32_t o_thw = cs.vec + 2 * vs;   // leapfrog position
-    uint32_t o_gw = cs.vec + 3 * vs;    // its gradient
-    T* const mom = sp<T>(cs.vec + 4 * vs);   // momentum
+    uint32_t o_a = cs.vec + 2 * vs;     // leapfrog positions (ping-pong)
+    uint32_t o_b = cs.vec + 3 * vs;
+    uint32_t o_gw = cs.vec + 4 * vs;    // gradient at the latest leapfrog position
+    T* const mom = sp<T>(cs.vec + 5 * vs);   // momentum
     const size_t chain = (size_t)b * a.C + c;
     const RngKey key{(uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), a.chain_id0 + (uint32_t)chain};
 
     Adapt<T> ad;
-    load_chain_state<T>(a, chain, sp<T>(o_thw), ad, tid, TS);
+    load_chain_state<T>(a, chain, sp<T>(o_a), ad, tid, TS);
     const int L = a.num_leapfrog;
     const double log_target = log(a.target_accept);
     T* draws = static_cast<T*>(a.draws) + chain * (size_t)a.num_results * P;
@@ -234,35 +255,33 @@ __global__ void SCCODA_BOUNDS(W) hmc_kernel(const __grid_constant__ KArgs a) {
         const bool boot = t < a.step_begin;
         const T eps = ad.eps;
         T kin = T(0);
-        T* const thw = sp<T>(o_thw);
-        T* const gw = sp<T>(o_gw);
-        const T* const thc = sp<T>(o_thc);
-        const T* const gc = sp<T>(o_gc);
         if (!boot) {
+            // momentum draw, first half kick and first drift: q1 = q0 + eps (p + eps/2 grad(q0))
+            const T* thc = sp<T>(o_thc);
+            const T* gc = sp<T>(o_gc);
+            T* qa = sp<T>(o_a);
 #pragma unroll 1
             for (int i = tid; i < P; i += TS) {
                 const T p = rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
                 kin += p * p;
-                thw[i] = thc[i];
-                mom[i] = fma(T(0.5) * eps, gc[i], p);
+                const T m = fma(T(0.5) * eps, gc[i], p);
+                mom[i] = m;
+                qa[i] = fma(eps, m, thc[i]);
             }
         }
+        g.sync();
+        uint32_t cur = o_a, nxt = o_b;
         const int nl = boot ? 1 : L;
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
-            if (!boot) {
-#pragma unroll 1
-                for (int i = tid; i < P; i += TS) thw[i] = fma(eps, mom[i], thw[i]);
-            }
-            g.sync();
-            dm_grad<T, W>(a.dm, dt, cs, o_thw, o_gw, g);
-            if (!boot) {
-                const T f = (l == L - 1) ? T(0.5) * eps : eps;
-#pragma unroll 1
-                for (int i = tid; i < P; i += TS) mom[i] = fma(f, gw[i], mom[i]);
+            const bool last = (l == nl - 1);
+            LeapfrogEpi<T> epi{sp<T>(o_gw), mom, sp<T>(cur), sp<T>(nxt), last ? T(0.5) * eps : eps, eps, !boot, !last};
+            dm_grad<T, W>(a.dm, dt, cs, cur, g, epi);
+            if (!last) {
+                const uint32_t tmp = cur; cur = nxt; nxt = tmp;
             }
         }
-        const double lp_new = dm_value<T, W>(a.dm, dt, cs, o_thw, g);
+        const double lp_new = dm_value<T, W>(a.dm, dt, cs, cur, g);
         bool acc = true;
         double lar = 0.0;
         if (!boot) {
@@ -276,8 +295,11 @@ __global__ void SCCODA_BOUNDS(W) hmc_kernel(const __grid_constant__ KArgs a) {
             acc = log(u) < lar;
         }
         if (acc) {
-            uint32_t tmp = o_thc; o_thc = o_thw; o_thw = tmp;
-            tmp = o_gc; o_gc = o_gw; o_gw = tmp;
+            // the proposal buffer becomes the current state; the old current buffer joins the ping-pong pair
+            const uint32_t old = o_thc;
+            o_thc = cur;
+            if (cur == o_a) o_a = old; else o_b = old;
+            const uint32_t tmp = o_gc; o_gc = o_gw; o_gw = tmp;
             lp_cur = lp_new;
         }
         if (boot) continue;
@@ -291,9 +313,9 @@ __global__ void SCCODA_BOUNDS(W) hmc_kernel(const __grid_constant__ KArgs a) {
         const int r = t - a.num_burnin;
         if (r >= 0 && a.store_draws) {
             T* dr = draws + (size_t)r * P;
-            const T* cur = sp<T>(o_thc);
+            const T* thc = sp<T>(o_thc);
 #pragma unroll 1
-            for (int i = tid; i < P; i += TS) dr[i] = cur[i];
+            for (int i = tid; i < P; i += TS) dr[i] = thc[i];
             if (tid == 0)
                 write_stats<T>(stats + (size_t)r * SCCODA_NSTAT, lp_cur, lar, acc, traced_eps, lar < -1000.0, L,
                                CUDART_NAN, false);
@@ -405,7 +427,7 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
                     }
                 }
                 g.sync();
-                dm_grad<T, W>(a.dm, dt, cs, o_q, o_gq, g);
+                dm_grad<T, W>(a.dm, dt, cs, o_q, g, StoreGrad<T>{gq});
                 lqv = dm_value<T, W>(a.dm, dt, cs, o_q, g);
                 if (boot) break;
                 T kk = T(0);

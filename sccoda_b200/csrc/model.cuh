@@ -84,7 +84,7 @@ struct ChainScratch {
     uint32_t cp;       // CPsi<T>[U,K] concentrations c_uk and digamma(c_uk)
     uint32_t rowterm;  // T[N]   digamma(S_u + n_n) - digamma(S_u)
     uint32_t G;        // T[NK]  d logp / d log c, element-list order
-    uint32_t Gu;       // T[U,K] per-group column sums of G
+    uint32_t Gu;       // T[U]   row sums S_u of the concentrations (small-U path)
     uint32_t beta;     // T[D,K] (reference column stays 0)
     uint32_t ind;      // T[D,K-1]
     uint32_t gk;       // T[(1+D),K]: row 0 = sum_n G_nk, row 1+d = sum_n x_nd G_nk
@@ -123,11 +123,27 @@ struct Group {
     }
 };
 
-// Gradient of the log-density at theta (theta/grad: shared-memory offsets of T[P]).  On return grad[] is
-// complete and visible to the whole group (trailing sync included); the scratch keeps c_uk for dm_value.
-template <typename T, int W>
+// Epilogue that only stores the gradient.
+template <typename T>
+struct StoreGrad {
+    T* grad;
+    __device__ __forceinline__ void operator()(int i, T gr) const { grad[i] = gr; }
+};
+
+// Gradient of the log-density at theta (shared-memory offset of T[P]).  Every component i of the gradient is
+// handed exactly once to epi(i, value) by the thread that owns it (the sampler fuses its leapfrog update there;
+// the epilogue may read theta[i] but must not write the theta buffer).  A trailing group sync makes everything
+// the epilogue wrote visible.  The scratch keeps c_uk for dm_value.
+//
+//   F1  columns k:   ind_dk = sigmoid(50 ind_raw), beta_dk = ind sigma_d b_offset              (:724-734)
+//   F2  (u, k):      c_uk = exp(alpha_k + x_u . beta_k), digamma(c_uk), S_u = sum_k c_uk         (:743)
+//   F3  rows n:      rowterm_n = digamma(S_u + n_n) - digamma(S_u)
+//   E   elements:    G_e = c (digamma(c + y) - digamma(c) - rowterm_n)
+//   B1  (r, k):      gk[r,k] = sum_n w_r(n) G_nk,  w_0 = 1, w_{1+d}(n) = x_nd
+//   B2  columns k:   chain rule to (alpha_k, b_offset_dk, ind_raw_dk), sigma_d by a group reduction
+template <typename T, int W, class Epi>
 __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
-                                        uint32_t theta_off, uint32_t grad_off, const Group<W>& g) {
+                                        uint32_t theta_off, const Group<W>& g, const Epi& epi) {
     const int tid = g.tid;
     constexpr int TS = Group<W>::SIZE;
     const int K = dm.K, D = dm.D, K1 = dm.K1, DK1 = dm.DK1, N = dm.N, U = dt.U, ref = dt.ref;
@@ -135,11 +151,10 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     const T* boff = sigma + D;
     const T* iraw = boff + DK1;
     const T* alpha = iraw + DK1;
-    T* grad = sp<T>(grad_off);
     CPsi<T>* cp = sp<CPsi<T>>(cs.cp);
     T* rowterm = sp<T>(cs.rowterm);
     T* G = sp<T>(cs.G);
-    T* Gu = sp<T>(cs.Gu);
+    T* Ssm = sp<T>(cs.Gu);  // [U] row sums of the concentrations (small-U path)
     T* beta = sp<T>(cs.beta);
     T* ind = sp<T>(cs.ind);
     T* gk = sp<T>(cs.gk);
@@ -149,61 +164,90 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     const int* rstart = sp<int>(dt.rstart);
     const int* colperm = sp<int>(dt.colperm);
 
-    // ---- phase 1: spike-and-slab effects  beta = sigmoid(50 ind_raw) * sigma_d * b_offset   (:724-734)
+    // ---- F1: spike-and-slab effects of the thread's own columns (read back by the same thread in F2: no sync)
 #pragma unroll 1
-    for (int i = tid; i < DK1; i += TS) {
-        const int d = fast_div(i, dm.magicK1);
-        const int j = i - d * K1;
-        const int k = j + (j >= ref);
-        const T id = sigmoid_stable(T(50) * iraw[i]);
-        ind[i] = id;
-        beta[d * K + k] = id * sigma[d] * boff[i];
-    }
-    g.sync();
-
-    // ---- phase 2: per covariate group  c_uk = exp(alpha_k + x_u . beta_k), digamma(c_uk)          (:743)
+    for (int k = tid; k < K; k += TS) {
+        if (k != ref) {
+            const int j = k - (k > ref);
 #pragma unroll 1
-    for (int e = tid; e < U * K; e += TS) {
-        const int u = fast_div(e, dm.magicK);
-        const int k = e - u * K;
-        T eta = alpha[k];
-#pragma unroll 2
-        for (int d = 0; d < D; ++d) eta = fma(xu[u * D + d], beta[d * K + k], eta);
-        CPsi<T> v;
-        v.c = exp_acc(eta);
-        v.psi = digamma_pos(v.c);
-        cp[e] = v;
-    }
-    g.sync();
-
-    // ---- phase 3: rows  S_u, digamma(S_u + n_n) - digamma(S_u)
-#pragma unroll 1
-    for (int n = tid; n < N; n += TS) {
-        const CPsi<T>* cu = cp + grp[n] * K;
-        T S0 = T(0), S1 = T(0);
-        int k = 0;
-#pragma unroll 2
-        for (; k + 1 < K; k += 2) {
-            S0 += cu[k].c;
-            S1 += cu[k + 1].c;
+            for (int d = 0; d < D; ++d) {
+                const int i = d * K1 + j;
+                const T id = sigmoid_stable(T(50) * iraw[i]);
+                ind[i] = id;
+                beta[d * K + k] = id * sigma[d] * boff[i];
+            }
         }
-        if (k < K) S0 += cu[k].c;
-        const T S = S0 + S1;
-        rowterm[n] = digamma_pos(S + ntot[n]) - digamma_pos(S);
+    }
+    // ---- F2 + F3
+    if (W == 1 && U <= 32) {
+        // few covariate groups, one warp: S_u by warp shuffles while the concentrations are produced
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {
+            T part = T(0);
+#pragma unroll 1
+            for (int k = tid; k < K; k += TS) {
+                T eta = alpha[k];
+#pragma unroll 1
+                for (int d = 0; d < D; ++d) eta = fma(xu[u * D + d], beta[d * K + k], eta);
+                CPsi<T> v;
+                v.c = exp_acc(eta);
+                v.psi = digamma_pos(v.c);
+                cp[u * K + k] = v;
+                part += v.c;
+            }
+            part = g.sum(part);
+            if (tid == 0) Ssm[u] = part;
+        }
+        g.sync();
+#pragma unroll 1
+        for (int n = tid; n < N; n += TS) {
+            const T S = Ssm[grp[n]];
+            rowterm[n] = digamma_pos(S + ntot[n]) - digamma_pos(S);
+        }
+    } else {
+#pragma unroll 1
+        for (int k = tid; k < K; k += TS) {
+            const T a = alpha[k];
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) {
+                T eta = a;
+#pragma unroll 1
+                for (int d = 0; d < D; ++d) eta = fma(xu[u * D + d], beta[d * K + k], eta);
+                CPsi<T> v;
+                v.c = exp_acc(eta);
+                v.psi = digamma_pos(v.c);
+                cp[u * K + k] = v;
+            }
+        }
+        g.sync();
+#pragma unroll 1
+        for (int n = tid; n < N; n += TS) {
+            const CPsi<T>* cu = cp + grp[n] * K;
+            T S0 = T(0), S1 = T(0);
+            int k = 0;
+#pragma unroll 2
+            for (; k + 1 < K; k += 2) {
+                S0 += cu[k].c;
+                S1 += cu[k + 1].c;
+            }
+            if (k < K) S0 += cu[k].c;
+            const T S = S0 + S1;
+            rowterm[n] = digamma_pos(S + ntot[n]) - digamma_pos(S);
+        }
     }
     g.sync();
 
-    // ---- phase 4: elements  G = c (digamma(c+y) - digamma(c) - rowterm_n)
+    // ---- E: elements  G = c (digamma(c+y) - digamma(c) - rowterm_n)
     if (dt.el_smem) {
         const Elem<T>* el = sp<Elem<T>>(dt.el);
-        // 4a: counts >= 6, no recurrence shift needed
+        // counts >= 6, no recurrence shift needed
 #pragma unroll 4
         for (int e = tid; e < dt.nbig; e += TS) {
             const Elem<T> v = el[e];
             const CPsi<T> q = cp[v.idx & 0xffffu];
             G[e] = q.c * (digamma_big(q.c + v.y) - q.psi - rowterm[v.idx >> 16]);
         }
-        // 4b: columns that contain small counts: general digamma
+        // columns that contain small counts: general digamma
 #pragma unroll 1
         for (int e = dt.nbig + tid; e < dm.NK; e += TS) {
             const Elem<T> v = el[e];
@@ -221,81 +265,55 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     }
     g.sync();
 
-    // ---- phase 5: per-group column sums  Gu_uk = sum_{n in u} G_nk   (element e = kk*N + n)
-#pragma unroll 1
-    for (int e = tid; e < U * K; e += TS) {
-        const int u = fast_div(e, dm.magicK);
-        const int kk = e - u * K;
-        const T* col = G + kk * N;
-        const int n1 = rstart[u + 1];
-        T s0 = T(0), s1 = T(0);
-        int n = rstart[u];
-#pragma unroll 2
-        for (; n + 1 < n1; n += 2) {
-            s0 += col[n];
-            s1 += col[n + 1];
-        }
-        if (n < n1) s0 += col[n];
-        Gu[u * K + colperm[kk]] = s0 + s1;
-    }
-    g.sync();
-
-    // ---- phase 6: gk[0,k] = sum_n G_nk ; gk[1+d,k] = sum_n x_nd G_nk
+    // ---- B1: gk[0,k] = sum_n G_nk ; gk[1+d,k] = sum_n x_nd G_nk   (column kk of the element list = G[kk*N ..])
 #pragma unroll 1
     for (int e = tid; e < (D + 1) * K; e += TS) {
         const int r = fast_div(e, dm.magicK);
-        const int k = e - r * K;
+        const int kk = e - r * K;
+        const T* col = G + kk * N;
         T s = T(0);
-        if (r == 0) {
+        int n = 0;
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {
+            const int n1 = rstart[u + 1];
+            T s0 = T(0), s1 = T(0);
 #pragma unroll 2
-            for (int u = 0; u < U; ++u) s += Gu[u * K + k];
-        } else {
-#pragma unroll 2
-            for (int u = 0; u < U; ++u) s = fma(xu[u * D + (r - 1)], Gu[u * K + k], s);
+            for (; n + 1 < n1; n += 2) {
+                s0 += col[n];
+                s1 += col[n + 1];
+            }
+            if (n < n1) s0 += col[n++];
+            const T w = (r == 0) ? T(1) : xu[u * D + (r - 1)];
+            s = fma(w, s0 + s1, s);
         }
-        gk[e] = s;
+        gk[r * K + colperm[kk]] = s;
     }
     g.sync();
 
-    // ---- phase 7: chain rule back to the unconstrained parameters
-    // 7a: d/d sigma_d (likelihood part) = sum_k g_dk ind_dk b_offset_dk — one group reduction per covariate,
-    //     kept by thread d (D <= 32 is checked on the host), which also owns parameter sigma_d below.
-    T my_sg = T(0);
+    // ---- B2: chain rule back to the unconstrained parameters, by column owner
 #pragma unroll 1
     for (int d = 0; d < D; ++d) {
+        const T s = sigma[d];
         T part = T(0);
 #pragma unroll 1
-        for (int j = tid; j < K1; j += TS) {
-            const int k = j + (j >= ref);
-            part = fma(gk[(1 + d) * K + k] * ind[d * K1 + j], boff[d * K1 + j], part);
+        for (int k = tid; k < K; k += TS) {
+            if (k != ref) {
+                const int i = d * K1 + k - (k > ref);
+                const T gg = gk[(1 + d) * K + k];
+                const T id = ind[i];
+                const T bo = boff[i];
+                const T t = gg * id;
+                epi(D + i, fma(t, s, -bo));                                              // d/d b_offset_dk
+                epi(D + DK1 + i, fma(t * s * bo, T(50) * (T(1) - id), -iraw[i]));        // d/d ind_raw_dk
+                part = fma(t, bo, part);
+            }
         }
+        // d/d sigma_d: sum_k g_dk ind_dk b_offset_dk - HalfCauchy term (zero prior gradient for sigma_d < 0 [TFP])
         part = g.sum(part);
-        if (tid == d) my_sg = part;
+        if (tid == 0) epi(d, part - (s >= T(0) ? T(2) * s / (T(1) + s * s) : T(0)));
     }
 #pragma unroll 1
-    for (int i = tid; i < dm.P; i += TS) {
-        T gr;
-        if (i < D) {
-            const T s = sigma[i];
-            // HalfCauchy on the unconstrained sigma_d: zero prior gradient for sigma_d < 0 [TFP]
-            gr = my_sg - (s >= T(0) ? T(2) * s / (T(1) + s * s) : T(0));
-        } else if (i < D + 2 * DK1) {
-            const bool is_off = i < D + DK1;
-            const int ii = is_off ? i - D : i - D - DK1;
-            const int d = fast_div(ii, dm.magicK1);
-            const int j = ii - d * K1;
-            const int k = j + (j >= ref);
-            const T gg = gk[(1 + d) * K + k];
-            const T id = ind[ii];
-            const T s = sigma[d];
-            if (is_off) gr = gg * id * s - boff[ii];
-            else gr = gg * s * boff[ii] * T(50) * id * (T(1) - id) - iraw[ii];
-        } else {
-            const int k = i - D - 2 * DK1;
-            gr = gk[k] - alpha[k] * T(0.04);
-        }
-        grad[i] = gr;
-    }
+    for (int k = tid; k < K; k += TS) epi(D + 2 * DK1 + k, fma(alpha[k], T(-0.04), gk[k]));     // d/d alpha_k
     g.sync();
 }
 
