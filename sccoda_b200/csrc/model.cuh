@@ -265,38 +265,70 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     }
     g.sync();
 
-    // ---- B1: gk[0,k] = sum_n G_nk ; gk[1+d,k] = sum_n x_nd G_nk   (column kk of the element list = G[kk*N ..])
+    // ---- B: column sums gk[0,k] = sum_n G_nk, gk[1+d,k] = sum_n x_nd G_nk and the chain rule
+    if (U <= 8) {
+        // few covariate groups: the owner of column k sums its whole column (rows are contiguous per group) and
+        // goes straight on to the parameters of that column — no barrier between the sums and the chain rule
 #pragma unroll 1
-    for (int e = tid; e < (D + 1) * K; e += TS) {
-        const int r = fast_div(e, dm.magicK);
-        const int kk = e - r * K;
-        const T* col = G + kk * N;
-        T s = T(0);
-        int n = 0;
+        for (int kk = tid; kk < K; kk += TS) {
+            const int k = colperm[kk];
+            const T* col = G + kk * N;
+            T g0 = T(0);
+            int n = 0;
 #pragma unroll 1
-        for (int u = 0; u < U; ++u) {
-            const int n1 = rstart[u + 1];
-            T s0 = T(0), s1 = T(0);
+            for (int u = 0; u < U; ++u) {
+                const int n1 = rstart[u + 1];
+                T s0 = T(0), s1 = T(0);
 #pragma unroll 2
-            for (; n + 1 < n1; n += 2) {
-                s0 += col[n];
-                s1 += col[n + 1];
+                for (; n + 1 < n1; n += 2) {
+                    s0 += col[n];
+                    s1 += col[n + 1];
+                }
+                if (n < n1) s0 += col[n++];
+                const T su = s0 + s1;
+                g0 += su;
+#pragma unroll 1
+                for (int d = 0; d < D; ++d) {
+                    const T prev = (u == 0) ? T(0) : gk[(1 + d) * K + k];
+                    gk[(1 + d) * K + k] = fma(xu[u * D + d], su, prev);
+                }
             }
-            if (n < n1) s0 += col[n++];
-            const T w = (r == 0) ? T(1) : xu[u * D + (r - 1)];
-            s = fma(w, s0 + s1, s);
+            gk[k] = g0;
         }
-        gk[r * K + colperm[kk]] = s;
+    } else {
+#pragma unroll 1
+        for (int e = tid; e < (D + 1) * K; e += TS) {
+            const int r = fast_div(e, dm.magicK);
+            const int kk = e - r * K;
+            const T* col = G + kk * N;
+            T s = T(0);
+            int n = 0;
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) {
+                const int n1 = rstart[u + 1];
+                T s0 = T(0), s1 = T(0);
+#pragma unroll 2
+                for (; n + 1 < n1; n += 2) {
+                    s0 += col[n];
+                    s1 += col[n + 1];
+                }
+                if (n < n1) s0 += col[n++];
+                const T w = (r == 0) ? T(1) : xu[u * D + (r - 1)];
+                s = fma(w, s0 + s1, s);
+            }
+            gk[r * K + colperm[kk]] = s;
+        }
+        g.sync();
     }
-    g.sync();
-
-    // ---- B2: chain rule back to the unconstrained parameters, by column owner
+    // Note on ownership: in the small-U path thread t produced gk[., colperm[kk]] for kk = t, t+TS, ...; the chain
+    // rule below is walked by sorted position too (k = colperm[kk]), so every thread consumes only its own sums.
 #pragma unroll 1
     for (int d = 0; d < D; ++d) {
         const T s = sigma[d];
         T part = T(0);
 #pragma unroll 1
-        for (int k = tid; k < K; k += TS) {
+        for (int kk = tid; kk < K; kk += TS) {
+            const int k = colperm[kk];
             if (k != ref) {
                 const int i = d * K1 + k - (k > ref);
                 const T gg = gk[(1 + d) * K + k];
@@ -313,7 +345,10 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
         if (tid == 0) epi(d, part - (s >= T(0) ? T(2) * s / (T(1) + s * s) : T(0)));
     }
 #pragma unroll 1
-    for (int k = tid; k < K; k += TS) epi(D + 2 * DK1 + k, fma(alpha[k], T(-0.04), gk[k]));     // d/d alpha_k
+    for (int kk = tid; kk < K; kk += TS) {
+        const int k = colperm[kk];
+        epi(D + 2 * DK1 + k, fma(alpha[k], T(-0.04), gk[k]));                            // d/d alpha_k
+    }
     g.sync();
 }
 
