@@ -112,7 +112,7 @@ typedef struct sccoda_sampler {
     uint32_t chain_id0;     /* global id of chain (b=0,c=0): lets shards on different GPUs keep disjoint streams */
     int32_t warps_per_chain; /* 0 = choose automatically; 1,2,4,8,16 */
     int32_t store_draws;    /* 1 = write draws/stats (default); 0 = only carry (e.g. warm-up chunks) */
-    int32_t reserved;
+    int32_t chains_per_cta; /* 0 = choose automatically; otherwise chain groups per thread block (tuning knob) */
 } sccoda_sampler;
 
 /* Library / device info. */

@@ -40,7 +40,7 @@ class Sampler(ctypes.Structure):
                 ("step_begin", ctypes.c_int32), ("step_end", ctypes.c_int32),
                 ("step_size", ctypes.c_double), ("target_accept", ctypes.c_double),
                 ("seed", ctypes.c_uint64), ("chain_id0", ctypes.c_uint32), ("warps_per_chain", ctypes.c_int32),
-                ("store_draws", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("store_draws", ctypes.c_int32), ("chains_per_cta", ctypes.c_int32)]
 
 
 _lib = None

@@ -72,7 +72,7 @@ struct Plan {
     int W, cpc, grid, smem;
 };
 
-int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int kind, int W_req, Plan* out) {
+int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int kind, int W_req, int cpc_req, Plan* out) {
     int dev = 0, max_smem = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
         cudaGetLastError();
@@ -92,7 +92,9 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int kind, int W_req, Pl
         if (W < 1) W = 1;
     }
     if (W != 1 && W != 2 && W != 4 && W != 8 && W != 16) return fail(-8, "warps_per_chain must be 0,1,2,4,8,16");
-    int cpc = 128 / (32 * W);
+    int cpc = cpc_req > 0 ? cpc_req : 128 / (32 * W);
+    const int cpc_cap = (W <= 4 ? 128 : 32 * W) / (32 * W);   // launch bounds of the kernels
+    if (cpc > cpc_cap) cpc = cpc_cap;
     if (cpc < 1) cpc = 1;
     if (cpc > p->C) cpc = p->C;
     // element list in shared memory: fp32 build only, and only while one chain group still fits
@@ -145,7 +147,7 @@ int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, in
     rc = fill_sampler(smp, a, &kind);
     if (rc) return rc;
     Plan pl;
-    rc = make_plan(prob, a, kind, smp->warps_per_chain, &pl);
+    rc = make_plan(prob, a, kind, smp->warps_per_chain, smp->chains_per_cta, &pl);
     if (rc) return rc;
     if (warps_per_chain) *warps_per_chain = pl.W;
     if (chains_per_cta) *chains_per_cta = pl.cpc;
@@ -162,7 +164,7 @@ int sccoda_logp_grad(const sccoda_problem* prob, const void* theta, double* logp
     fill_dims(prob, a);
     a.init = theta; a.draws = grad; a.carry = logp;
     Plan pl;
-    rc = make_plan(prob, a, sccoda::KIND_LOGP, 0, &pl);
+    rc = make_plan(prob, a, sccoda::KIND_LOGP, 0, 0, &pl);
     if (rc) return rc;
     CUDA_TRY(sccoda::launch_kernel(sccoda::KIND_LOGP, prob->dtype, pl.W, pl.cpc, a, static_cast<cudaStream_t>(stream)));
     return 0;
@@ -182,7 +184,7 @@ int sccoda_sample(const sccoda_problem* prob, const sccoda_sampler* smp, const v
     if (a.store_draws && (!draws || !stats)) return fail(-23, "draws/stats must not be NULL when store_draws != 0");
     a.init = init; a.draws = draws; a.stats = stats; a.carry = carry;
     Plan pl;
-    rc = make_plan(prob, a, kind, smp->warps_per_chain, &pl);
+    rc = make_plan(prob, a, kind, smp->warps_per_chain, smp->chains_per_cta, &pl);
     if (rc) return rc;
     CUDA_TRY(sccoda::launch_kernel(kind, prob->dtype, pl.W, pl.cpc, a, static_cast<cudaStream_t>(stream)));
     return 0;

@@ -23,6 +23,7 @@ ap.add_argument("--results", type=int, default=100)
 ap.add_argument("--burnin", type=int, default=20)
 ap.add_argument("--method", type=int, default=0)
 ap.add_argument("--W", type=int, default=0)
+ap.add_argument("--cpc", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--step-size", type=float, default=0.02)
 a = ap.parse_args()
@@ -31,7 +32,7 @@ x, y, _ = generate_sweep(a.datasets, K=a.K, n_per_group=a.n_per_group)
 pk = pack(x, y, a.K - 1, dtype=np.float32)
 init = sch.initial_states(a.datasets, a.chains, 1, a.K, seed=1).astype(np.float32)
 prob = DeviceProblem(pk, chains=a.chains)
-smp = prob.make_sampler(a.method, a.results, a.burnin, step_size=a.step_size, seed=3, warps_per_chain=a.W)
+smp = prob.make_sampler(a.method, a.results, a.burnin, step_size=a.step_size, seed=3, warps_per_chain=a.W, chains_per_cta=a.cpc)
 for _ in range(a.reps):
     out = prob.sample(init, smp)
 ge = a.datasets * a.chains * (a.results + a.burnin) * 10
