@@ -383,10 +383,16 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
         if (s >= 0.0) lp -= log1p(s * s);
     }
     // DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c)                               (:746-751)
+    // Guard (documented deviation): beyond c_max the lgamma differences have lost all
+    // precision (the reference's fp64 graph then evaluates to the bare multinomial constant, a spurious mode
+    // thousands of nats above the posterior that traps the chain); such states get a NaN value => rejected.
+    const T c_max = sizeof(T) == 4 ? T(1e6) : T(1e15);
 #pragma unroll 1
     for (int e = tid; e < U * K; e += TS) {
         const int u = fast_div(e, dm.magicK);
-        lp -= (double)((T)(rstart[u + 1] - rstart[u]) * lgamma_pos(cp[e].c));
+        const T c = cp[e].c;
+        lp -= (double)((T)(rstart[u + 1] - rstart[u]) * lgamma_pos(c));
+        if (!(c <= c_max)) lp = CUDART_NAN;
     }
 #pragma unroll 1
     for (int n = tid; n < dm.N; n += TS) {
