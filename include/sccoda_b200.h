@@ -137,9 +137,12 @@ int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, in
                        int32_t* chains_per_cta, int32_t* grid, int32_t* smem_bytes);
 
 /* Host-buffer convenience (the end-to-end path): all pointers are HOST memory; copies in, runs on `device`,
- * copies draws/stats (either may be NULL) and, if summary != NULL, the summaries back.  Synchronous. */
+ * copies draws/stats (either may be NULL) and, if summary != NULL, the summaries back.  Synchronous.
+ * The device workspace (inputs + draw buffer) is cached across calls; sccoda_release_workspace() frees it. */
 int sccoda_sample_host(const sccoda_problem* prob_host, const sccoda_sampler* smp, const void* init, void* draws,
                        void* stats, double* summary, int32_t summary_skip, int32_t device, float* kernel_ms);
+
+int sccoda_release_workspace(void);
 
 /* Measurement utility for the bench: FP32 FFMA peak (TFLOP/s, 2 flop per FMA) and MUFU peak (T op/s) of the
  * current device, from two register-resident micro-kernels (best of 5). Synchronises `stream`. */

@@ -20,7 +20,7 @@ NCARRY = 8
 NSUM_PARAM, NSUM_BETA, NSUM_SCALAR = 2, 4, 6
 
 EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sample", "sccoda_summarize",
-           "sccoda_launch_plan", "sccoda_sample_host", "sccoda_measure_peaks")
+           "sccoda_launch_plan", "sccoda_sample_host", "sccoda_release_workspace", "sccoda_measure_peaks")
 
 
 class Problem(ctypes.Structure):

@@ -129,11 +129,46 @@ int fill_sampler(const sccoda_sampler* s, sccoda::KArgs& a, int* kind) {
     return 0;
 }
 
+// Device workspace of sccoda_sample_host, kept across calls (per device): the draw buffer of a sweep is tens of
+// GB and cudaMalloc/cudaFree of it would otherwise sit inside every end-to-end call.
+struct Workspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int device = -1;
+};
+Workspace g_ws;
+
+int workspace_get(int device, size_t bytes, void** out) {
+    if (g_ws.ptr != nullptr && (g_ws.device != device || g_ws.bytes < bytes)) {
+        cudaFree(g_ws.ptr);
+        g_ws = Workspace{};
+    }
+    if (g_ws.ptr == nullptr) {
+        if (cudaMalloc(&g_ws.ptr, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            g_ws = Workspace{};
+            return fail(-42, "cudaMalloc(workspace, %zu bytes) failed", bytes);
+        }
+        g_ws.bytes = bytes;
+        g_ws.device = device;
+    }
+    *out = g_ws.ptr;
+    return 0;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
 }  // namespace
 
 extern "C" {
 
 int sccoda_version(void) { return 100; }
+
+int sccoda_release_workspace(void) {
+    if (g_ws.ptr != nullptr) cudaFree(g_ws.ptr);
+    g_ws = Workspace{};
+    return 0;
+}
 
 const char* sccoda_last_error(void) { return g_err; }
 
@@ -203,68 +238,68 @@ int sccoda_summarize(const sccoda_problem* prob, int32_t num_results, int32_t sk
 
 int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, const void* init, void* draws, void* stats,
                        double* summary, int32_t summary_skip, int32_t device, float* kernel_ms) {
-    if (!ph || !smp) return fail(-40, "NULL argument");
+    if (!ph || !smp || !init) return fail(-40, "NULL argument");
     if (ph->B < 1 || ph->C < 1 || ph->N < 1 || ph->K < 2 || ph->D < 1 || ph->Umax < 1) return fail(-41, "bad problem dimensions");
+    if (smp->num_results < 1) return fail(-12, "need num_results >= 1");
     CUDA_TRY(cudaSetDevice(device));
     const size_t ts = ph->dtype == SCCODA_F64 ? 8 : 4;
     const size_t B = ph->B, C = ph->C, N = ph->N, K = ph->K, D = ph->D, U = ph->Umax, S = smp->num_results;
     const size_t P = D + 2 * D * (K - 1) + K;
-    struct Buf { void** dp; const void* hp; size_t bytes; };
-    sccoda_problem pd = *ph;
-    void *d_y = nullptr, *d_ycst = nullptr, *d_eidx = nullptr, *d_colperm = nullptr, *d_nbig = nullptr, *d_ntot = nullptr,
-         *d_xu = nullptr, *d_grp = nullptr, *d_rstart = nullptr, *d_U = nullptr, *d_ref = nullptr, *d_lconst = nullptr,
-         *d_init = nullptr, *d_draws = nullptr, *d_stats = nullptr, *d_sum = nullptr;
-    Buf in[] = {{&d_y, ph->ey, B * N * K * ts}, {&d_ycst, ph->eycst, B * N * K * ts}, {&d_eidx, ph->eidx, B * N * K * 4},
-                {&d_colperm, ph->colperm, B * K * 4}, {&d_nbig, ph->nbig, B * 4}, {&d_ntot, ph->ntot, B * N * ts},
-                {&d_xu, ph->xu, B * U * D * ts}, {&d_grp, ph->grp, B * N * 4}, {&d_rstart, ph->rstart, B * (U + 1) * 4},
-                {&d_U, ph->U, B * 4}, {&d_ref, ph->ref, B * 4}, {&d_lconst, ph->lconst, B * 8},
-                {&d_init, init, B * C * P * ts}};
-    std::vector<void*> to_free;
-    auto cleanup = [&]() { for (void* p : to_free) cudaFree(p); };
+    const size_t nsum = SCCODA_NSUM_PARAM * P + SCCODA_NSUM_BETA * D * K + SCCODA_NSUM_SCALAR;
+    // one workspace, carved into 256-byte aligned pieces
+    struct Piece { const void* host; size_t bytes; size_t off; };
+    Piece in[] = {{ph->ey, B * N * K * ts, 0}, {ph->eycst, B * N * K * ts, 0}, {ph->eidx, B * N * K * 4, 0},
+                  {ph->colperm, B * K * 4, 0}, {ph->nbig, B * 4, 0}, {ph->ntot, B * N * ts, 0}, {ph->xu, B * U * D * ts, 0},
+                  {ph->grp, B * N * 4, 0}, {ph->rstart, B * (U + 1) * 4, 0}, {ph->U, B * 4, 0}, {ph->ref, B * 4, 0},
+                  {ph->lconst, B * 8, 0}, {init, B * C * P * ts, 0}};
+    size_t off = 0;
+    for (auto& p : in) {
+        if (!p.host) return fail(-7, "problem has a NULL array");
+        p.off = off;
+        off += align256(p.bytes);
+    }
+    const size_t draws_bytes = B * C * S * P * ts, stats_bytes = B * C * S * SCCODA_NSTAT * ts, sum_bytes = B * C * nsum * 8;
+    const size_t o_draws = off; off += align256(draws_bytes);
+    const size_t o_stats = off; off += align256(stats_bytes);
+    const size_t o_sum = off; off += align256(sum_bytes);
+    void* base = nullptr;
+    int rc = workspace_get(device, off, &base);
+    if (rc) return rc;
+    char* w = static_cast<char*>(base);
     cudaStream_t st;
     CUDA_TRY(cudaStreamCreate(&st));
-    int rc = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     do {
-        for (auto& b : in) {
-            if (cudaMalloc(b.dp, b.bytes) != cudaSuccess) { rc = fail(-42, "cudaMalloc(%zu) failed", b.bytes); break; }
-            to_free.push_back(*b.dp);
-            if (cudaMemcpyAsync(*b.dp, b.hp, b.bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail(-43, "H2D copy failed"); break; }
-        }
-        if (rc) break;
-        const size_t draws_bytes = B * C * S * P * ts, stats_bytes = B * C * S * SCCODA_NSTAT * ts;
-        const size_t nsum = SCCODA_NSUM_PARAM * P + SCCODA_NSUM_BETA * D * K + SCCODA_NSUM_SCALAR;
-        if (cudaMalloc(&d_draws, draws_bytes) != cudaSuccess) { rc = fail(-42, "cudaMalloc(draws, %zu) failed", draws_bytes); break; }
-        to_free.push_back(d_draws);
-        if (cudaMalloc(&d_stats, stats_bytes) != cudaSuccess) { rc = fail(-42, "cudaMalloc(stats) failed"); break; }
-        to_free.push_back(d_stats);
-        pd.ey = d_y; pd.eycst = d_ycst; pd.eidx = (const uint32_t*)d_eidx; pd.colperm = (const int32_t*)d_colperm;
-        pd.nbig = (const int32_t*)d_nbig; pd.ntot = d_ntot; pd.xu = d_xu; pd.grp = (const int32_t*)d_grp;
-        pd.rstart = (const int32_t*)d_rstart; pd.U = (const int32_t*)d_U; pd.ref = (const int32_t*)d_ref;
-        pd.lconst = (const double*)d_lconst;
+        bool ok = true;
+        for (auto& p : in)
+            ok = ok && cudaMemcpyAsync(w + p.off, p.host, p.bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        if (!ok) { rc = fail(-43, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        sccoda_problem pd = *ph;
+        pd.ey = w + in[0].off; pd.eycst = w + in[1].off; pd.eidx = (const uint32_t*)(w + in[2].off);
+        pd.colperm = (const int32_t*)(w + in[3].off); pd.nbig = (const int32_t*)(w + in[4].off);
+        pd.ntot = w + in[5].off; pd.xu = w + in[6].off; pd.grp = (const int32_t*)(w + in[7].off);
+        pd.rstart = (const int32_t*)(w + in[8].off); pd.U = (const int32_t*)(w + in[9].off);
+        pd.ref = (const int32_t*)(w + in[10].off); pd.lconst = (const double*)(w + in[11].off);
         sccoda_sampler s2 = *smp;
         s2.step_begin = 0; s2.step_end = 0; s2.store_draws = 1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, st);
-        rc = sccoda_sample(&pd, &s2, d_init, d_draws, d_stats, nullptr, st);
+        rc = sccoda_sample(&pd, &s2, w + in[12].off, w + o_draws, w + o_stats, nullptr, st);
         if (rc) break;
         cudaEventRecord(e1, st);
         if (summary) {
-            if (cudaMalloc(&d_sum, B * C * nsum * 8) != cudaSuccess) { rc = fail(-42, "cudaMalloc(summary) failed"); break; }
-            to_free.push_back(d_sum);
-            rc = sccoda_summarize(&pd, (int32_t)S, summary_skip, d_draws, d_stats, (double*)d_sum, st);
+            rc = sccoda_summarize(&pd, (int32_t)S, summary_skip, w + o_draws, w + o_stats, (double*)(w + o_sum), st);
             if (rc) break;
-            cudaMemcpyAsync(summary, d_sum, B * C * nsum * 8, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(summary, w + o_sum, sum_bytes, cudaMemcpyDeviceToHost, st);
         }
-        if (draws) cudaMemcpyAsync(draws, d_draws, draws_bytes, cudaMemcpyDeviceToHost, st);
-        if (stats) cudaMemcpyAsync(stats, d_stats, stats_bytes, cudaMemcpyDeviceToHost, st);
+        if (draws) cudaMemcpyAsync(draws, w + o_draws, draws_bytes, cudaMemcpyDeviceToHost, st);
+        if (stats) cudaMemcpyAsync(stats, w + o_stats, stats_bytes, cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = fail(-44, "kernel/copy failed: %s", cudaGetErrorString(e)); break; }
         if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
     } while (0);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    cleanup();
     cudaStreamDestroy(st);
     return rc;
 }
