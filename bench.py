@@ -139,7 +139,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -229,7 +229,7 @@ def run_ours(a):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world == 1 and a.gpus > 1:
-        print(json.dumps({"error": f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks"}), flush=True)
+        emit({"error": f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks"})
         sys.exit(2)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -396,7 +396,7 @@ def run_ours(a):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "ess": ess_info,
             "gpu_launches": 2 * a.steps, "clocks": clock_info,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     comm.close()
 
 
@@ -404,8 +404,26 @@ def out_plan(prob, smp):
     return prob.plan(smp)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Write the ONE JSON line to the real stdout (everything else — NCCL banners, warnings — goes to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     a = parse_args()
+    # keep stdout clean: C libraries (NCCL) print banners to fd 1
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
