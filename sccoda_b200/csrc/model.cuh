@@ -266,9 +266,73 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     g.sync();
 
     // ---- B: column sums gk[0,k] = sum_n G_nk, gk[1+d,k] = sum_n x_nd G_nk and the chain rule
+    if (U <= 8 && K <= TS && D <= 4) {
+        // Register-resident fast path (few covariate groups, one column per thread): thread kk sums its whole
+        // column (rows are contiguous per group), keeps the (1+D) sums in registers and goes straight on to the
+        // parameters of that column; only the sigma_d reduction crosses threads.
+        const bool has = tid < K;
+        const int k = colperm[has ? tid : 0];
+        T g0 = T(0);
+        T acc[4] = {T(0), T(0), T(0), T(0)};
+        if (has) {
+            const T* p = G + tid * N;
+            int n = 0;
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) {
+                const int n1 = rstart[u + 1];
+                const int cnt = n1 - n;
+                n = n1;
+                T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+#pragma unroll 1
+                for (int q = cnt >> 2; q > 0; --q, p += 4) {
+                    s0 += p[0];
+                    s1 += p[1];
+                    s2 += p[2];
+                    s3 += p[3];
+                }
+                if (cnt & 2) {
+                    s0 += p[0];
+                    s1 += p[1];
+                    p += 2;
+                }
+                if (cnt & 1) {
+                    s2 += p[0];
+                    p += 1;
+                }
+                const T su = (s0 + s1) + (s2 + s3);
+                g0 += su;
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                    if (d < D) acc[d] = fma(xu[u * D + d], su, acc[d]);
+            }
+        }
+        const bool active = has && (k != ref);
+        const int j = k - (k > ref);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (d < D) {
+                const T s = sigma[d];
+                T part = T(0);
+                if (active) {
+                    const int i = d * K1 + j;
+                    const T id = ind[i];
+                    const T bo = boff[i];
+                    const T t = acc[d] * id;
+                    epi(D + i, fma(t, s, -bo));                                          // d/d b_offset_dk
+                    epi(D + DK1 + i, fma(t * s * bo, T(50) * (T(1) - id), -iraw[i]));    // d/d ind_raw_dk
+                    part = t * bo;
+                }
+                // d/d sigma_d: sum_k g_dk ind_dk b_offset_dk - HalfCauchy term (zero prior gradient below 0 [TFP])
+                part = g.sum(part);
+                if (tid == 0) epi(d, part - (s >= T(0) ? T(2) * s / (T(1) + s * s) : T(0)));
+            }
+        }
+        if (has) epi(D + 2 * DK1 + k, fma(alpha[k], T(-0.04), g0));                     // d/d alpha_k
+        g.sync();
+        return;
+    }
     if (U <= 8) {
-        // few covariate groups: the owner of column k sums its whole column (rows are contiguous per group) and
-        // goes straight on to the parameters of that column — no barrier between the sums and the chain rule
+        // few covariate groups, several columns per thread: same walk, sums parked in shared memory
 #pragma unroll 1
         for (int kk = tid; kk < K; kk += TS) {
             const int k = colperm[kk];
