@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsccoda_b200.so")
+# SCCODA_B200_LIB overrides the library path (development builds, e.g. ablation variants)
+LIB_PATH = os.environ.get("SCCODA_B200_LIB") or os.path.join(_HERE, "libsccoda_b200.so")
 
 F32, F64 = 0, 1
 METHOD_HMC, METHOD_HMC_DA, METHOD_NUTS = 0, 1, 2

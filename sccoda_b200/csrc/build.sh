@@ -3,8 +3,8 @@
 # The translation units are compiled in parallel and linked into one shared library.
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-out="${here}/../libsccoda_b200.so"
-obj="${here}/build"
+out="${SCCODA_LIB_OUT:-${here}/../libsccoda_b200.so}"
+obj="${SCCODA_OBJ_DIR:-${here}/build}"
 mkdir -p "${obj}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${SCCODA_NVCC_EXTRA:-})

@@ -179,7 +179,12 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
         }
     }
     // ---- F2 + F3
+#ifdef SCCODA_ABLATE_F
+    if (false) {
+    } else if (false) {
+#else
     if (W == 1 && U <= 32) {
+#endif
         // few covariate groups, one warp: S_u by warp shuffles while the concentrations are produced
 #pragma unroll 1
         for (int u = 0; u < U; ++u) {
@@ -238,7 +243,11 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     g.sync();
 
     // ---- E: elements  G = c (digamma(c+y) - digamma(c) - rowterm_n)
+#ifdef SCCODA_ABLATE_E
+    if (false) {
+#else
     if (dt.el_smem) {
+#endif
         const Elem<T>* el = sp<Elem<T>>(dt.el);
         // counts >= 6, no recurrence shift needed
 #pragma unroll 4
@@ -257,7 +266,11 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     } else {
         // element list streamed from global memory (fp64 parity build, or tiles too large for shared memory)
 #pragma unroll 1
+#ifdef SCCODA_ABLATE_E
+        for (int e = tid; e < 0; e += TS) {
+#else
         for (int e = tid; e < dm.NK; e += TS) {
+#endif
             const uint32_t ix = dt.eidx[e];
             const CPsi<T> q = cp[ix & 0xffffu];
             G[e] = q.c * (digamma_pos(q.c + dt.ey[e]) - q.psi - rowterm[ix >> 16]);
@@ -274,7 +287,11 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
         const int k = colperm[has ? tid : 0];
         T g0 = T(0);
         T acc[4] = {T(0), T(0), T(0), T(0)};
+#ifdef SCCODA_ABLATE_B
+        if (false) {
+#else
         if (has) {
+#endif
             const T* p = G + tid * N;
             int n = 0;
 #pragma unroll 1
@@ -434,15 +451,22 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     const int* grp = sp<int>(dt.grp);
     const T* ntot = sp<T>(dt.ntot);
     double lp = 0.0;
+#ifdef SCCODA_ABLATE_VALUE
+    return g.sum(lp) + (double)sigma[0] * 1e-30;
+#endif
+    // priors: HalfCauchy(0,1) on sigma_d (:703-707), Normal(0,1) on b_offset / ind_raw (:709-722), Normal(0,5) on
+    // alpha (:736-741); the theta-independent constants live in dt.lconst
+    {
+        T acc = T(0);
 #pragma unroll 1
-    for (int i = tid; i < DK1; i += TS) {                                             // Normal(0,1) x2 (:709-722)
-        const T bo = boff[i], ir = iraw[i];
-        lp += (double)(T(-0.5) * (bo * bo + ir * ir));
+        for (int i = D + tid; i < dm.P; i += TS) {
+            const T v = sigma[i];                                   // theta[i]
+            acc = fma(v * v, i < D + 2 * DK1 ? T(-0.5) : T(-0.02), acc);
+        }
+        lp += (double)acc;
     }
 #pragma unroll 1
-    for (int k = tid; k < K; k += TS) lp += (double)(alpha[k] * alpha[k] * T(-0.02));  // Normal(0,5)   (:736-741)
-#pragma unroll 1
-    for (int d = tid; d < D; d += TS) {                                                // HalfCauchy(0,1) (:703-707)
+    for (int d = tid; d < D; d += TS) {
         const double s = (double)sigma[d];
         if (s >= 0.0) lp -= log1p(s * s);
     }
@@ -451,25 +475,50 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     // precision (the reference's fp64 graph then evaluates to the bare multinomial constant, a spurious mode
     // thousands of nats above the posterior that traps the chain); such states get a NaN value => rejected.
     const T c_max = sizeof(T) == 4 ? T(1e6) : T(1e15);
+    {
+        T acc = T(0);
+        bool bad = false;
 #pragma unroll 1
-    for (int e = tid; e < U * K; e += TS) {
-        const int u = fast_div(e, dm.magicK);
-        const T c = cp[e].c;
-        lp -= (double)((T)(rstart[u + 1] - rstart[u]) * lgamma_pos(c));
-        if (!(c <= c_max)) lp = CUDART_NAN;
+        for (int e = tid; e < U * K; e += TS) {
+            const int u = fast_div(e, dm.magicK);
+            const T c = cp[e].c;
+            acc = fma(-(T)(rstart[u + 1] - rstart[u]), lgamma_pos(c), acc);
+            bad = bad || !(c <= c_max);
+        }
+        lp += (double)acc;
+        if (bad) lp = CUDART_NAN;
     }
 #pragma unroll 1
     for (int n = tid; n < dm.N; n += TS) {
         const CPsi<T>* cu = cp + grp[n] * K;
         T S = T(0);
-#pragma unroll 1
+#pragma unroll 4
         for (int k = 0; k < K; ++k) S += cu[k].c;
-        lp += lgamma_f64((double)S) - lgamma_f64((double)S + (double)ntot[n]);
+        lp += lgamma_rowdiff_f64((double)S, (double)ntot[n]);
     }
+    // elements: lgamma(c + y) - lgamma(y); per-thread partial sums in T (<= a few dozen terms), total in fp64
+    {
+        T acc = T(0);
+        if (dt.el_smem) {
+            const Elem<T>* el = sp<Elem<T>>(dt.el);
+#pragma unroll 2
+            for (int e = tid; e < dt.nbig; e += TS) {
+                const Elem<T> v = el[e];
+                acc += lgamma_shift_big(cp[v.idx & 0xffffu].c, v.y, dt.eycst[e]);
+            }
 #pragma unroll 1
-    for (int e = tid; e < dm.NK; e += TS) {
-        const uint32_t ix = dt.eidx[e];
-        lp += (double)lgamma_shift(cp[ix & 0xffffu].c, dt.ey[e], sizeof(T) == 4 ? dt.eycst[e] : T(0));
+            for (int e = dt.nbig + tid; e < dm.NK; e += TS) {
+                const Elem<T> v = el[e];
+                acc += lgamma_shift(cp[v.idx & 0xffffu].c, v.y, dt.eycst[e]);   // mixed columns: branch on y
+            }
+            lp += (double)acc;
+        } else {
+#pragma unroll 1
+            for (int e = tid; e < dm.NK; e += TS) {
+                const uint32_t ix = dt.eidx[e];
+                lp += (double)lgamma_shift(cp[ix & 0xffffu].c, dt.ey[e], sizeof(T) == 4 ? dt.eycst[e] : T(0));
+            }
+        }
     }
     lp = g.sum(lp) + dt.lconst;
     // HalfCauchy support: -inf as soon as one sigma_d < 0 [TFP]; every thread scans the D values (uniform)
