@@ -249,9 +249,30 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     if (dt.el_smem) {
 #endif
         const Elem<T>* el = sp<Elem<T>>(dt.el);
-        // counts >= 6, no recurrence shift needed
-#pragma unroll 4
-        for (int e = tid; e < dt.nbig; e += TS) {
+        // counts >= 6, no recurrence shift needed.  Full batches of EB elements per thread are written
+        // loads-first / stores-last: the arrays share one shared-memory buffer, so the compiler would otherwise
+        // keep every element's loads behind the previous element's store (no ILP inside the warp).
+        constexpr int EB = 4;
+        int e0 = tid;
+#pragma unroll 1
+        for (; e0 + (EB - 1) * TS < dt.nbig; e0 += EB * TS) {
+            Elem<T> v[EB];
+            CPsi<T> q[EB];
+            T rt[EB];
+#pragma unroll
+            for (int j = 0; j < EB; ++j) v[j] = el[e0 + j * TS];
+#pragma unroll
+            for (int j = 0; j < EB; ++j) {
+                q[j] = cp[v[j].idx & 0xffffu];
+                rt[j] = rowterm[v[j].idx >> 16];
+            }
+#pragma unroll
+            for (int j = 0; j < EB; ++j) rt[j] = q[j].c * (digamma_big(q[j].c + v[j].y) - q[j].psi - rt[j]);
+#pragma unroll
+            for (int j = 0; j < EB; ++j) G[e0 + j * TS] = rt[j];
+        }
+#pragma unroll 1
+        for (int e = e0; e < dt.nbig; e += TS) {
             const Elem<T> v = el[e];
             const CPsi<T> q = cp[v.idx & 0xffffu];
             G[e] = q.c * (digamma_big(q.c + v.y) - q.psi - rowterm[v.idx >> 16]);

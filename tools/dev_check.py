@@ -1,7 +1,7 @@
 """Development helper (run on the GPU box): prints K1 parity errors and quick HMC numbers."""
-import sys, time
+import os, sys, time
 import numpy as np
-sys.path.insert(0, "tests")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from conftest import haber_salm, random_states, synthetic_dataset
 from oracle import np_oracle as o, c_oracle as co
 from sccoda_b200.engine import DeviceProblem
