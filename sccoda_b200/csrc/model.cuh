@@ -121,6 +121,21 @@ struct Group {
         }
         return v;
     }
+    // group-wide OR of a predicate
+    __device__ __forceinline__ bool any(bool v) const {
+        v = __any_sync(0xffffffffu, v) != 0;
+        if (W > 1) {
+            int* r = sp<int>(red);
+            sync();
+            if ((tid & 31) == 0) r[tid >> 5] = v ? 1 : 0;
+            sync();
+            int o = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) o |= r[w];
+            v = o != 0;
+        }
+        return v;
+    }
 };
 
 // Epilogue that only stores the gradient.
@@ -454,6 +469,27 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     g.sync();
 }
 
+// Correction of this thread's element terms for concentrations >= c_joint (rare: far tails / nearly multinomial
+// data): replaces the standard form by the joint cancellation-free form (special.cuh), which also carries the
+// -lgamma(c) that dm_value skipped for those concentrations.  Out of line: the common path keeps its small code.
+template <typename T, int W>
+__device__ __noinline__ double value_joint_fixup(const Dims& dm, const DataTile<T>& dt, const CPsi<T>* cp, T c_joint,
+                                                 int tid) {
+    constexpr int TS = Group<W>::SIZE;
+    double fix = 0.0;
+#pragma unroll 1
+    for (int e = tid; e < dm.NK; e += TS) {
+        const uint32_t ix = dt.eidx[e];
+        const T c = cp[ix & 0xffffu].c;
+        if (c >= c_joint) {
+            const T yc = sizeof(T) == 4 ? dt.eycst[e] : T(0);
+            const T y = dt.ey[e];
+            fix += (double)lgamma_joint(c, y, yc) - (double)lgamma_shift(c, y, yc);
+        }
+    }
+    return fix;
+}
+
 // Value of the log-density at theta.  Must follow dm_grad at the same theta (uses the c_uk it left in the
 // scratch).  Terms are evaluated in T, accumulated in fp64; the two O(n ln n)-sized row terms are taken in
 // fp64.  Every thread of the group receives the result.
@@ -496,6 +532,10 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     // precision (the reference's fp64 graph then evaluates to the bare multinomial constant, a spurious mode
     // thousands of nats above the posterior that traps the chain); such states get a NaN value => rejected.
     const T c_max = sizeof(T) == 4 ? T(1e6) : T(1e15);
+    // fp32: concentrations >= c_joint switch to the joint (cancellation-free) form, which already contains
+    // -lgamma(c); never taken in the fp64 build
+    const T c_joint = sizeof(T) == 4 ? T(SCCODA_C_JOINT) : T(SCCODA_C_JOINT_F64);
+    bool need_fix = false;   // some concentration >= c_joint (rare); made group-uniform below
     {
         T acc = T(0);
         bool bad = false;
@@ -503,7 +543,8 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
         for (int e = tid; e < U * K; e += TS) {
             const int u = fast_div(e, dm.magicK);
             const T c = cp[e].c;
-            acc = fma(-(T)(rstart[u + 1] - rstart[u]), lgamma_pos(c), acc);
+            if (c < c_joint) acc = fma(-(T)(rstart[u + 1] - rstart[u]), lgamma_pos(c), acc);
+            else need_fix = true;
             bad = bad || !(c <= c_max);
         }
         lp += (double)acc;
@@ -512,12 +553,22 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
 #pragma unroll 1
     for (int n = tid; n < dm.N; n += TS) {
         const CPsi<T>* cu = cp + grp[n] * K;
-        T S = T(0);
-#pragma unroll 4
-        for (int k = 0; k < K; ++k) S += cu[k].c;
-        lp += lgamma_rowdiff_f64((double)S, (double)ntot[n]);
+        // S in fp32 pairs, combined in fp64 (the conversions are the expensive part of an fp64 accumulation)
+        T S0 = T(0), S1 = T(0), S2 = T(0), S3 = T(0);
+        int k = 0;
+#pragma unroll 1
+        for (; k + 3 < K; k += 4) {
+            S0 += cu[k].c;
+            S1 += cu[k + 1].c;
+            S2 += cu[k + 2].c;
+            S3 += cu[k + 3].c;
+        }
+#pragma unroll 1
+        for (; k < K; ++k) S0 += cu[k].c;
+        lp += lgamma_rowdiff_f64(((double)S0 + (double)S1) + ((double)S2 + (double)S3), (double)ntot[n]);
     }
-    // elements: lgamma(c + y) - lgamma(y); per-thread partial sums in T (<= a few dozen terms), total in fp64
+    // elements: lgamma(c + y) - lgamma(y); per-thread partial sums in T (<= a few dozen terms), total in fp64.
+    // Concentrations >= c_joint (rare) are patched afterwards by value_joint_fixup (out of line).
     {
         T acc = T(0);
         if (dt.el_smem) {
@@ -541,6 +592,8 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
             }
         }
     }
+    // every thread owns a different slice of the elements in the fix-up: the flag must be uniform over the group
+    if (sizeof(T) == 4 && g.any(need_fix)) lp += value_joint_fixup<T, W>(dm, dt, cp, c_joint, tid);
     lp = g.sum(lp) + dt.lconst;
     // HalfCauchy support: -inf as soon as one sigma_d < 0 [TFP]; every thread scans the D values (uniform)
     for (int d = 0; d < D; ++d)

@@ -113,6 +113,21 @@ __device__ __forceinline__ float lgamma_shift(float c, float y, float ycst) {
     return y >= 6.0f ? lgamma_shift_big(c, y, ycst) : lgamma_shift_small(c, y, ycst);
 }
 
+// Large concentrations (c >= SCCODA_C_JOINT): h(c, y) = lgamma(c + y) - lgamma(c) - lgamma(y) evaluated jointly,
+// so that the O(c ln c) parts of lgamma(c+y) and lgamma(c) never appear (fp32 would lose them):
+//   y >= 6: (c-1/2) log1p(y/c) + (y-1/2) log1p(c/y) + ln(z)/2 - ln(2 pi)/2 + r(z) - r(c) - r(y)   [ycst = r(y)]
+//   y <  6: (c-1/2) log1p(y/c) + y (ln z - 1) + r(z) - r(c) - lgamma(y)                           [ycst = lgamma(y)]
+#define SCCODA_C_JOINT 64.0f
+__device__ __forceinline__ float lgamma_joint(float c, float y, float ycst) {
+    const float z = c + y;
+    const float rc = rcp_fast(c);
+    const float lz = log_fast(z);
+    const float a = (c - 0.5f) * log1p_pos(y * rc);
+    const float rem = stirling_rem(rcp_fast(z)) - stirling_rem(rc) - ycst;
+    if (y >= 6.0f) return a + fmaf(y - 0.5f, log1p_pos(c * rcp_fast(y)), fmaf(0.5f, lz, -SCCODA_HALF_LN_2PI_F)) + rem;
+    return a + fmaf(y, lz - 1.0f, rem);
+}
+
 __device__ __forceinline__ float sigmoid_stable(float s) {
     // == exp(s)/(1+exp(s)) (scCODA_model.py:724-725) wherever that is finite; no overflow for large |s|
     const float e = ex2_fast(-fabsf(s) * SCCODA_LOG2EF);
@@ -159,6 +174,8 @@ static __device__ __noinline__ double lgamma_f64(double x) {
 __device__ __forceinline__ double lgamma_pos(double x) { return lgamma_f64(x); }
 // fp64: ycst = 0 and the host constant carries nothing extra — plain lgamma(c+y).
 __device__ __forceinline__ double lgamma_shift(double c, double y, double ycst) { return lgamma_f64(c + y) - ycst; }
+#define SCCODA_C_JOINT_F64 1e300
+__device__ __forceinline__ double lgamma_joint(double c, double y, double ycst) { return lgamma_f64(c + y) - lgamma_f64(c) - ycst; }
 __device__ __forceinline__ double lgamma_shift_big(double c, double y, double ycst) { return lgamma_f64(c + y) - ycst; }
 __device__ __forceinline__ double lgamma_shift_small(double c, double y, double ycst) { return lgamma_f64(c + y) - ycst; }
 
