@@ -39,6 +39,23 @@
  *   ref     [B] i32     reference cell type (scCODA_model.py:688)
  *   lconst  [B] f64     all parameter-independent terms of the log-density
  *
+ * Pair / item layout of the gradient pass (used when `grouped` != 0; built by sccoda_b200/_pack.py: build_items,
+ * consumed by csrc/grouped.cuh).  A pair is (covariate group u, cell type k), index u*K + k, or the row totals of a
+ * group ("total pair", index Umax*K + u); NP = Umax*(K+1).  Counts >= 6 of a pair are stored SCCODA_ITEM_R at a
+ * time in items (padded with 6); counts in {1..5} are folded into the pair's rational; the remaining counts below 6
+ * (the 0.5 pseudocount, non-integer data) are "odd" counts, grouped per pair.  Every item and every odd group owns
+ * one of the NF result slots of its pair (slot pair*NF + t; padding entries point at the spare slot NP*NF).
+ *   NI      [B] i32     number of items of dataset b (<= NImax)
+ *   iy      [B,SCCODA_ITEM_R,NImax]  counts of the items (slot-major, so that consecutive items are contiguous)
+ *   ipair   [B,NImax] u16    pair of each item
+ *   ipos    [B,NImax] u16    result slot of each item
+ *   pcoef   [B,NP,6]    numerators (a0,b0,a1,b1,a2,b2) of  sum_i W_i/(c+i) = (a0 c+b0)/(c(c+5)) + (a1 c+b1)/((c+1)(c+4))
+ *                       + (a2 c+b2)/((c+2)(c+3)),  W_i = #counts>=6 + #odd + #{counts in {1..5} that exceed i}
+ *   NG      [B] i32     number of odd groups of dataset b (<= NGmax)
+ *   oy      [B,NOmax]   odd counts, the counts of one group consecutive
+ *   opair, opos [B,NGmax] u16   pair and result slot of each odd group
+ *   odesc   [B,NGmax] u32       first odd count | n_odd << 16
+ *
  * State vector (P = D + 2 D (K-1) + K), order of scCODA_model.py:692-693:
  *   [ sigma_d (D) | b_offset (D,K-1) | ind_raw (D,K-1) | alpha (K) ]
  */
@@ -53,6 +70,8 @@ extern "C" {
 
 #define SCCODA_F32 0
 #define SCCODA_F64 1
+
+#define SCCODA_ITEM_R 5 /* counts per item of the pair / item layout */
 
 #define SCCODA_METHOD_HMC 0    /* HMC + SimpleStepSizeAdaptation          (sample_hmc,    :276-289) */
 #define SCCODA_METHOD_HMC_DA 1 /* HMC + DualAveragingStepSizeAdaptation   (sample_hmc_da, :382-395) */
@@ -83,6 +102,10 @@ typedef struct sccoda_problem {
     int32_t N, K, D, Umax; /* samples, cell types, covariates, max covariate groups */
     int32_t dtype;         /* SCCODA_F32 / SCCODA_F64 */
     int32_t nbig_min;      /* min over datasets of nbig[b] (host copy; sizes the shared-memory fallback loop) */
+    int32_t grouped;       /* 1: gradient by pairs / items (few covariate groups); 0: by single counts */
+    int32_t NImax, NOmax;  /* item / odd-count slots per dataset (grouped layout; 0 when unused) */
+    int32_t NGmax, NF;     /* odd-group slots per dataset; result slots per pair (power of two >= 2) */
+    int32_t reserved0;
     const void* ey;
     const void* eycst;
     const uint32_t* eidx;
@@ -95,6 +118,17 @@ typedef struct sccoda_problem {
     const int32_t* U;
     const int32_t* ref;
     const double* lconst;
+    /* pair / item layout; may all be NULL when grouped == 0 */
+    const int32_t* NI;
+    const void* iy;
+    const uint16_t* ipair;
+    const uint16_t* ipos;
+    const void* pcoef;
+    const int32_t* NG;
+    const void* oy;
+    const uint16_t* opair;
+    const uint16_t* opos;
+    const uint32_t* odesc;
 } sccoda_problem;
 
 typedef struct sccoda_sampler {
@@ -113,6 +147,7 @@ typedef struct sccoda_sampler {
     int32_t warps_per_chain; /* 0 = choose automatically; 1,2,4,8,16 */
     int32_t store_draws;    /* 1 = write draws/stats (default); 0 = only carry (e.g. warm-up chunks) */
     int32_t chains_per_cta; /* 0 = choose automatically; otherwise chain groups per thread block (tuning knob) */
+    int32_t generic_only;   /* 1 = never dispatch to a shape-specialised kernel (the case/control HMC kernel); 0 = default */
 } sccoda_sampler;
 
 /* Library / device info. */
@@ -135,6 +170,10 @@ int sccoda_summarize(const sccoda_problem* prob, int32_t num_results, int32_t sk
 /* Bytes of dynamic shared memory and threads per CTA the sampler would use (for planning / tests). */
 int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* warps_per_chain,
                        int32_t* chains_per_cta, int32_t* grid, int32_t* smem_bytes);
+
+/* Which kernel sccoda_sample would launch: 1 = generic HMC, 2 = NUTS, 3 = case/control HMC specialisation
+ * (D == 1, <= 2 covariate groups, K <= 32, NF <= 4, fp32, one warp per chain, grouped layout). */
+int sccoda_kernel_kind(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* kind);
 
 /* Host-buffer convenience (the end-to-end path): all pointers are HOST memory; copies in, runs on `device`,
  * copies draws/stats (either may be NULL) and, if summary != NULL, the summaries back.  Synchronous.

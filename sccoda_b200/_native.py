@@ -21,18 +21,34 @@ NCARRY = 8
 NSUM_PARAM, NSUM_BETA, NSUM_SCALAR = 2, 4, 6
 
 EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sample", "sccoda_summarize",
-           "sccoda_launch_plan", "sccoda_sample_host", "sccoda_release_workspace", "sccoda_measure_peaks")
+           "sccoda_launch_plan", "sccoda_kernel_kind", "sccoda_sample_host", "sccoda_release_workspace", "sccoda_measure_peaks")
 
 
 class Problem(ctypes.Structure):
     _fields_ = [("B", ctypes.c_int32), ("C", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
                 ("D", ctypes.c_int32), ("Umax", ctypes.c_int32), ("dtype", ctypes.c_int32),
                 ("nbig_min", ctypes.c_int32),
+                ("grouped", ctypes.c_int32), ("NImax", ctypes.c_int32), ("NOmax", ctypes.c_int32),
+                ("NGmax", ctypes.c_int32), ("NF", ctypes.c_int32), ("reserved0", ctypes.c_int32),
                 ("ey", ctypes.c_void_p), ("eycst", ctypes.c_void_p), ("eidx", ctypes.c_void_p),
                 ("colperm", ctypes.c_void_p), ("nbig", ctypes.c_void_p),
                 ("ntot", ctypes.c_void_p), ("xu", ctypes.c_void_p),
                 ("grp", ctypes.c_void_p), ("rstart", ctypes.c_void_p), ("U", ctypes.c_void_p),
-                ("ref", ctypes.c_void_p), ("lconst", ctypes.c_void_p)]
+                ("ref", ctypes.c_void_p), ("lconst", ctypes.c_void_p),
+                ("NI", ctypes.c_void_p), ("iy", ctypes.c_void_p), ("ipair", ctypes.c_void_p),
+                ("ipos", ctypes.c_void_p), ("pcoef", ctypes.c_void_p), ("NG", ctypes.c_void_p),
+                ("oy", ctypes.c_void_p), ("opair", ctypes.c_void_p), ("opos", ctypes.c_void_p),
+                ("odesc", ctypes.c_void_p)]
+
+
+def problem_fields(pk, ptr):
+    """Keyword arguments of Problem(...) for a PackedProblem; ptr(array_or_tensor) -> address."""
+    names = ("ey", "eycst", "eidx", "colperm", "nbig", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst",
+             "NI", "iy", "ipair", "ipos", "pcoef", "NG", "oy", "opair", "opos", "odesc")
+    kw = dict(B=pk.B, N=pk.N, K=pk.K, D=pk.D, Umax=pk.Umax, dtype=F32 if pk.dtype.itemsize == 4 else F64,
+              nbig_min=pk.nbig_min, grouped=pk.grouped, NImax=pk.NImax, NOmax=pk.NOmax, NGmax=pk.NGmax, NF=pk.NF)
+    kw.update({n: ptr(n) for n in names})
+    return kw
 
 
 class Sampler(ctypes.Structure):
@@ -41,7 +57,8 @@ class Sampler(ctypes.Structure):
                 ("step_begin", ctypes.c_int32), ("step_end", ctypes.c_int32),
                 ("step_size", ctypes.c_double), ("target_accept", ctypes.c_double),
                 ("seed", ctypes.c_uint64), ("chain_id0", ctypes.c_uint32), ("warps_per_chain", ctypes.c_int32),
-                ("store_draws", ctypes.c_int32), ("chains_per_cta", ctypes.c_int32)]
+                ("store_draws", ctypes.c_int32), ("chains_per_cta", ctypes.c_int32),
+                ("generic_only", ctypes.c_int32)]
 
 
 _lib = None
@@ -65,6 +82,7 @@ def lib() -> ctypes.CDLL:
         _lib.sccoda_sample.argtypes = [pp, sp, vp, vp, vp, vp, vp]
         _lib.sccoda_summarize.argtypes = [pp, i32, i32, vp, vp, vp, vp]
         _lib.sccoda_launch_plan.argtypes = [pp, sp] + [ctypes.POINTER(i32)] * 4
+        _lib.sccoda_kernel_kind.argtypes = [pp, sp, ctypes.POINTER(i32)]
         _lib.sccoda_sample_host.argtypes = [pp, sp, vp, vp, vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float)]
         _lib.sccoda_measure_peaks.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), vp]
     return _lib

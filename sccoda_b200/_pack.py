@@ -44,6 +44,26 @@ class PackedProblem:
     lconst: np.ndarray   # [B] float64
     row_order: np.ndarray  # [B,N] original row index of each packed row
     logp_const: np.ndarray  # [B] multinomial-coefficient constant (float64), for reference
+    # ---- grouped ("pair / item") layout of the gradient pass, see build_items() --------------------------------
+    grouped: int = 0                 # 1: the kernels take the pair/item gradient path
+    NImax: int = 0                   # item slots per dataset (even)
+    NOmax: int = 0                   # odd-count slots per dataset (>= 1)
+    NGmax: int = 0                   # odd-group slots per dataset (>= 1)
+    NF: int = 0                      # result slots per pair (power of two >= 2): its items + its odd group
+    NI: np.ndarray = None            # [B] int32 items of dataset b
+    NG: np.ndarray = None            # [B] int32 odd groups of dataset b
+    iy: np.ndarray = None            # [B,ITEM_R,NImax] counts >= 6 of each item, padded with 6
+    ipair: np.ndarray = None         # [B,NImax] uint16 pair of each item
+    ipos: np.ndarray = None          # [B,NImax] uint16 result slot of each item: pair*NF + t
+    pcoef: np.ndarray = None         # [B,NP,6] rational coefficients of each pair, NP = Umax*(K+1)
+    oy: np.ndarray = None            # [B,NOmax] counts < 6 that are not in {0,1,...,5}
+    opair: np.ndarray = None         # [B,NGmax] uint16 pair of each odd group
+    opos: np.ndarray = None          # [B,NGmax] uint16 result slot of each odd group
+    odesc: np.ndarray = None         # [B,NGmax] uint32 first odd count | n_odd << 16
+
+    @property
+    def NP(self) -> int:
+        return self.Umax * (self.K + 1)
 
     @property
     def P(self) -> int:
@@ -58,8 +78,108 @@ def apply_pseudocount(y: np.ndarray) -> np.ndarray:
     return y
 
 
-def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True) -> PackedProblem:
-    """x: [B,N,D] or [N,D]; y: [B,N,K] or [N,K]; ref: int or [B]."""
+ITEM_R = 5  # counts per item (SCCODA_ITEM_R in include/sccoda_b200.h)
+
+
+def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndarray, Umax: int):
+    """Pair / item layout of the gradient pass (csrc/grouped.cuh).
+
+    A *pair* is (covariate group u, cell type k): all rows of the group share the concentration c_uk, so
+    sum_{n in u} [psi(c + y_nk) - psi(c)] only depends on the multiset of counts of the pair.  The row totals form
+    one more pair per group ("total pair", index Umax*K + u, concentration S_u = sum_k c_uk).  Per pair:
+      * counts >= 6 go, ITEM_R at a time, into *items* (padded with 6, which contributes psi(c+6) - psi(c+6) = 0);
+        an item yields sum_j [psi(c + y_j) - psi(c + 6)] with one log of a product and no recurrence shift;
+      * counts in {1,...,5} and the items' reference point psi(c+6) - psi(c) = sum_{i<6} 1/(c+i) are folded into
+        six weights W_i >= 0 of sum_i W_i / (c + i), stored as the numerators of three quadratics
+        (c(c+5), (c+1)(c+4), (c+2)(c+3));  counts equal to 0 contribute nothing;
+      * any other count below 6 (the 0.5 pseudocount, non-integer data) is an *odd* count, evaluated one by one;
+        the odd counts of one pair form an *odd group*.
+    Every item / odd group owns one of the NF result slots of its pair (slot index pair*NF + t).
+    Returns a dict of float64 / integer arrays (see include/sccoda_b200.h for the layout).
+    """
+    B, N, K = ys.shape
+    R = ITEM_R
+    NP = Umax * (K + 1)
+    ext = np.concatenate([ys, ntot[:, :, None]], axis=2)                      # [B,N,K+1]: last column = row totals
+    pcoef = np.zeros((B, NP, 6))
+    per_ds = []
+    nslot_max = 1
+    for b in range(B):
+        yb, pb, tb, ob, opb, otb, odb = [], [], [], [], [], [], []
+        n_odd = 0
+        for u in range(int(U[b])):
+            blk = ext[b, rstart[b, u]:rstart[b, u + 1]]                       # [cnt,K+1]
+            pair = np.where(np.arange(K + 1) < K, u * K + np.arange(K + 1), Umax * K + u)
+            big = blk >= 6.0
+            is_int = (blk == np.floor(blk)) & (blk >= 1.0) & ~big
+            odd = ~big & ~is_int & (blk != 0.0)
+            nb = big.sum(axis=0)
+            no = odd.sum(axis=0)
+            W = np.stack([nb + no + (is_int & (blk > i)).sum(axis=0) for i in range(6)], axis=1).astype(np.float64)
+            pcoef[b, pair] = np.stack([W[:, 0] + W[:, 5], 5.0 * W[:, 0], W[:, 1] + W[:, 4], 4.0 * W[:, 1] + W[:, 4],
+                                       W[:, 2] + W[:, 3], 3.0 * W[:, 2] + 2.0 * W[:, 3]], axis=1)
+            nf = -(-nb // R)
+            nslot_max = max(nslot_max, int((nf + (no > 0)).max()))
+            # columns sorted by decreasing count: the big ones come first, everything else becomes padding
+            srt = -np.sort(-np.where(big, blk, 6.0), axis=0)
+            depth = int(nf.max()) * R
+            if depth > srt.shape[0]:
+                srt = np.concatenate([srt, np.full((depth - srt.shape[0], K + 1), 6.0)], axis=0)
+            if depth:
+                chunks = srt[:depth].reshape(depth // R, R, K + 1)            # [t, j, col]
+                tt, cc = np.nonzero(np.arange(depth // R)[:, None] < nf[None, :])
+                order = np.lexsort((tt, cc))                                  # pair-major, items of a pair consecutive
+                tt, cc = tt[order], cc[order]
+                yb.append(chunks[tt, :, cc])
+                pb.append(pair[cc])
+                tb.append(tt)
+            if no.any():
+                rr, cc = np.nonzero(odd.T)                                    # rr = column, cc = row (column-major)
+                ob.append(blk[cc, rr])
+                cols = np.nonzero(no)[0]
+                opb.append(pair[cols])
+                otb.append(nf[cols])                                          # slot of the group: after the items
+                odb.append((n_odd + np.r_[0, np.cumsum(no[cols])[:-1]]) | (no[cols] << 16))
+                n_odd += int(no.sum())
+        cat = lambda lst, shape, dt: np.concatenate(lst).astype(dt) if lst else np.zeros(shape, dt)
+        per_ds.append((cat(yb, (0, R), np.float64), cat(pb, (0,), np.int64), cat(tb, (0,), np.int64),
+                       cat(ob, (0,), np.float64), cat(opb, (0,), np.int64), cat(otb, (0,), np.int64),
+                       cat(odb, (0,), np.int64)))
+    NF = 2
+    while NF < nslot_max:
+        NF *= 2
+    NI = np.array([d[1].size for d in per_ds], dtype=np.int32)
+    NG = np.array([d[4].size for d in per_ds], dtype=np.int32)
+    NImax = int(NI.max()) if B else 0
+    NImax = max(2, NImax + (NImax & 1))
+    NOmax = max(1, max(d[3].size for d in per_ds) if B else 1)
+    NGmax = max(1, int(NG.max()) if B else 1)
+    if NP * NF > 65535 or NImax > 65535 or NOmax > 65535:
+        raise ValueError("pair/item layout needs Umax*(K+1)*NF <= 65535 and at most 65535 items / odd counts")
+    iy = np.full((B, R, NImax), 6.0)
+    ipair = np.zeros((B, NImax), dtype=np.uint16)
+    ipos = np.full((B, NImax), NP * NF, dtype=np.uint16)                      # padding items write to a spare slot
+    oy = np.full((B, NOmax), 1.0)
+    opair = np.zeros((B, NGmax), dtype=np.uint16)
+    opos = np.full((B, NGmax), NP * NF, dtype=np.uint16)
+    odesc = np.zeros((B, NGmax), dtype=np.uint32)
+    for b, (yb, pb, tb, ob, opb, otb, odb) in enumerate(per_ds):
+        iy[b, :, :NI[b]] = yb.T
+        ipair[b, :NI[b]] = pb
+        ipos[b, :NI[b]] = pb * NF + tb
+        oy[b, :ob.size] = ob
+        opair[b, :NG[b]] = opb
+        opos[b, :NG[b]] = opb * NF + otb
+        odesc[b, :NG[b]] = odb
+    return dict(NF=NF, NImax=NImax, NOmax=NOmax, NGmax=NGmax, NI=NI, NG=NG, iy=iy, ipair=ipair, ipos=ipos, pcoef=pcoef,
+                oy=oy, opair=opair, opos=opos, odesc=odesc)
+
+
+def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) -> PackedProblem:
+    """x: [B,N,D] or [N,D]; y: [B,N,K] or [N,K]; ref: int or [B].
+
+    grouped: None = choose (pair/item gradient path when the covariate groups are large enough that the item
+    padding stays below 60 % of the counts), True / False = force."""
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
     if y.ndim == 2:
@@ -126,7 +246,15 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True) -> PackedProblem
     eycst = ycst[bidx, rows, perm].reshape(B, N * K)
     uk = grp[:, None, :].astype(np.int64) * K + perm                          # [B,K,N]
     eidx = (uk | (rows.astype(np.int64) << 16)).astype(np.uint32).reshape(B, N * K)
-    return PackedProblem(B=B, N=N, K=K, D=D, Umax=Umax, dtype=dtype,
+    it = build_items(ys, ntot, rstart, U, Umax)
+    if grouped is None:
+        grouped = bool(ITEM_R * int(it["NI"].max()) <= 1.6 * N * (K + 1))
+    return PackedProblem(grouped=int(bool(grouped)), NImax=it["NImax"], NOmax=it["NOmax"], NGmax=it["NGmax"],
+                         NF=it["NF"], NI=it["NI"], NG=it["NG"], iy=np.ascontiguousarray(it["iy"], dtype),
+                         ipair=it["ipair"], ipos=it["ipos"], pcoef=np.ascontiguousarray(it["pcoef"], dtype),
+                         oy=np.ascontiguousarray(it["oy"], dtype), opair=it["opair"], opos=it["opos"],
+                         odesc=it["odesc"],
+                         B=B, N=N, K=K, D=D, Umax=Umax, dtype=dtype,
                          ey=np.ascontiguousarray(ey, dtype), eycst=np.ascontiguousarray(eycst, dtype),
                          eidx=np.ascontiguousarray(eidx), colperm=np.ascontiguousarray(colperm),
                          nbig=nbig, nbig_min=int(nbig.min()),

@@ -53,6 +53,15 @@ int validate(const sccoda_problem* p) {
     if (!p->ey || !p->eycst || !p->eidx || !p->colperm || !p->nbig || !p->ntot || !p->xu || !p->grp || !p->rstart ||
         !p->U || !p->ref || !p->lconst)
         return fail(-7, "problem has a NULL array");
+    if (p->grouped) {
+        if (p->NImax < 2 || (p->NImax & 1) || p->NImax > 65535 || p->NOmax < 1 || p->NOmax > 65535 || p->NGmax < 1)
+            return fail(-6, "grouped layout needs an even 2 <= NImax <= 65535, 1 <= NOmax <= 65535 and NGmax >= 1 (got %d, %d, %d)",
+                        p->NImax, p->NOmax, p->NGmax);
+        if (p->NF < 2 || (p->NF & (p->NF - 1))) return fail(-6, "grouped layout needs NF = power of two >= 2 (got %d)", p->NF);
+        if ((uint64_t)p->Umax * (p->K + 1) * p->NF > 65535ull) return fail(-6, "grouped layout needs Umax*(K+1)*NF <= 65535");
+        if (!p->NI || !p->iy || !p->ipair || !p->ipos || !p->pcoef || !p->NG || !p->oy || !p->opair || !p->opos || !p->odesc)
+            return fail(-7, "grouped problem has a NULL pair/item array");
+    }
     return 0;
 }
 
@@ -66,13 +75,18 @@ void fill_dims(const sccoda_problem* p, sccoda::KArgs& a) {
     a.ey = p->ey; a.eycst = p->eycst; a.eidx = p->eidx; a.colperm = p->colperm; a.nbig = p->nbig;
     a.ntot = p->ntot; a.xu = p->xu;
     a.grp = p->grp; a.rstart = p->rstart; a.U = p->U; a.ref = p->ref; a.lconst = p->lconst;
+    a.grouped = p->grouped ? 1 : 0;
+    a.NImax = a.grouped ? p->NImax : 0; a.NOmax = a.grouped ? p->NOmax : 0;
+    a.NGmax = a.grouped ? p->NGmax : 0; a.NF = a.grouped ? p->NF : 0;
+    a.NI = p->NI; a.iy = p->iy; a.ipair = p->ipair; a.ipos = p->ipos; a.pcoef = p->pcoef;
+    a.NG = p->NG; a.oy = p->oy; a.opair = p->opair; a.opos = p->opos; a.odesc = p->odesc;
 }
 
 struct Plan {
     int W, cpc, grid, smem;
 };
 
-int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int kind, int W_req, int cpc_req, Plan* out) {
+int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, int cpc_req, Plan* out) {
     int dev = 0, max_smem = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
         cudaGetLastError();
@@ -92,6 +106,7 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int kind, int W_req, in
         if (W < 1) W = 1;
     }
     if (W != 1 && W != 2 && W != 4 && W != 8 && W != 16) return fail(-8, "warps_per_chain must be 0,1,2,4,8,16");
+    kind = sccoda::select_kind(a, kind, p->dtype, W);   // specialised kernels (may need less shared memory)
     int cpc = cpc_req > 0 ? cpc_req : 128 / (32 * W);
     const int cpc_cap = (W <= 4 ? 128 : 32 * W) / (32 * W);   // launch bounds of the kernels
     if (cpc > cpc_cap) cpc = cpc_cap;
@@ -124,6 +139,7 @@ int fill_sampler(const sccoda_sampler* s, sccoda::KArgs& a, int* kind) {
     if (a.step_begin < 0 || a.step_end > s->num_burnin + s->num_results || a.step_begin > a.step_end)
         return fail(-16, "bad step range [%d,%d)", a.step_begin, a.step_end);
     a.store_draws = s->store_draws;
+    a.generic_only = s->generic_only ? 1 : 0;
     a.step_size = s->step_size; a.target_accept = s->target_accept; a.seed = s->seed; a.chain_id0 = s->chain_id0;
     *kind = s->method == SCCODA_METHOD_NUTS ? sccoda::KIND_NUTS : sccoda::KIND_HMC;
     return 0;
@@ -191,6 +207,21 @@ int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, in
     return 0;
 }
 
+int sccoda_kernel_kind(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* kind_out) {
+    int rc = validate(prob);
+    if (rc) return rc;
+    sccoda::KArgs a{};
+    fill_dims(prob, a);
+    int kind = 0;
+    rc = fill_sampler(smp, a, &kind);
+    if (rc) return rc;
+    Plan pl;
+    rc = make_plan(prob, a, kind, smp->warps_per_chain, smp->chains_per_cta, &pl);
+    if (rc) return rc;
+    if (kind_out) *kind_out = kind;
+    return 0;
+}
+
 int sccoda_logp_grad(const sccoda_problem* prob, const void* theta, double* logp, void* grad, void* stream) {
     int rc = validate(prob);
     if (rc) return rc;
@@ -199,9 +230,10 @@ int sccoda_logp_grad(const sccoda_problem* prob, const void* theta, double* logp
     fill_dims(prob, a);
     a.init = theta; a.draws = grad; a.carry = logp;
     Plan pl;
-    rc = make_plan(prob, a, sccoda::KIND_LOGP, 0, 0, &pl);
+    int kind = sccoda::KIND_LOGP;
+    rc = make_plan(prob, a, kind, 0, 0, &pl);
     if (rc) return rc;
-    CUDA_TRY(sccoda::launch_kernel(sccoda::KIND_LOGP, prob->dtype, pl.W, pl.cpc, a, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(sccoda::launch_kernel(kind, prob->dtype, pl.W, pl.cpc, a, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 
@@ -252,12 +284,24 @@ int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, cons
                   {ph->colperm, B * K * 4, 0}, {ph->nbig, B * 4, 0}, {ph->ntot, B * N * ts, 0}, {ph->xu, B * U * D * ts, 0},
                   {ph->grp, B * N * 4, 0}, {ph->rstart, B * (U + 1) * 4, 0}, {ph->U, B * 4, 0}, {ph->ref, B * 4, 0},
                   {ph->lconst, B * 8, 0}, {init, B * C * P * ts, 0}};
+    const size_t NP = U * (K + 1), NIm = ph->grouped ? (size_t)ph->NImax : 0, NOm = ph->grouped ? (size_t)ph->NOmax : 0,
+                 NGm = ph->grouped ? (size_t)ph->NGmax : 0;
+    Piece gin[] = {{ph->NI, B * 4, 0}, {ph->iy, B * SCCODA_ITEM_R * NIm * ts, 0}, {ph->ipair, B * NIm * 2, 0},
+                   {ph->ipos, B * NIm * 2, 0}, {ph->pcoef, B * NP * 6 * ts, 0}, {ph->NG, B * 4, 0},
+                   {ph->oy, B * NOm * ts, 0}, {ph->opair, B * NGm * 2, 0}, {ph->opos, B * NGm * 2, 0},
+                   {ph->odesc, B * NGm * 4, 0}};
     size_t off = 0;
     for (auto& p : in) {
         if (!p.host) return fail(-7, "problem has a NULL array");
         p.off = off;
         off += align256(p.bytes);
     }
+    if (ph->grouped)
+        for (auto& p : gin) {
+            if (!p.host) return fail(-7, "grouped problem has a NULL pair/item array");
+            p.off = off;
+            off += align256(p.bytes);
+        }
     const size_t draws_bytes = B * C * S * P * ts, stats_bytes = B * C * S * SCCODA_NSTAT * ts, sum_bytes = B * C * nsum * 8;
     const size_t o_draws = off; off += align256(draws_bytes);
     const size_t o_stats = off; off += align256(stats_bytes);
@@ -273,8 +317,17 @@ int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, cons
         bool ok = true;
         for (auto& p : in)
             ok = ok && cudaMemcpyAsync(w + p.off, p.host, p.bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        if (ph->grouped)
+            for (auto& p : gin)
+                ok = ok && cudaMemcpyAsync(w + p.off, p.host, p.bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
         if (!ok) { rc = fail(-43, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         sccoda_problem pd = *ph;
+        if (ph->grouped) {
+            pd.NI = (const int32_t*)(w + gin[0].off); pd.iy = w + gin[1].off; pd.ipair = (const uint16_t*)(w + gin[2].off);
+            pd.ipos = (const uint16_t*)(w + gin[3].off); pd.pcoef = w + gin[4].off; pd.NG = (const int32_t*)(w + gin[5].off);
+            pd.oy = w + gin[6].off; pd.opair = (const uint16_t*)(w + gin[7].off); pd.opos = (const uint16_t*)(w + gin[8].off);
+            pd.odesc = (const uint32_t*)(w + gin[9].off);
+        }
         pd.ey = w + in[0].off; pd.eycst = w + in[1].off; pd.eidx = (const uint32_t*)(w + in[2].off);
         pd.colperm = (const int32_t*)(w + in[3].off); pd.nbig = (const int32_t*)(w + in[4].off);
         pd.ntot = w + in[5].off; pd.xu = w + in[6].off; pd.grp = (const int32_t*)(w + in[7].off);

@@ -8,12 +8,21 @@ namespace sccoda {
 int nvec_for(int kind, int max_depth) {
     if (kind == KIND_LOGP) return 2;
     if (kind == KIND_HMC) return 6;
+    if (kind == KIND_HMC_CC) return 1;
     return 15 + 2 * (max_depth + 1);
+}
+
+int select_kind(const KArgs& a, int kind, int dtype, int W) {
+    if (kind == KIND_HMC && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 && a.dm.D == 1 && a.Umax <= 2 &&
+        a.dm.K <= 32 && a.NF <= 4)
+        return KIND_HMC_CC;
+    return kind;
 }
 
 size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int dtype) {
     const size_t ts = dtype == SCCODA_F64 ? 8 : 4;
-    const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem, nvec_for(kind, a.max_depth), W, ts);
+    const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem, a.grouped ? a.NImax : 0, a.NF,
+                                  nvec_for(kind, a.max_depth), W, ts);
     return pl.data_total + (size_t)chains_per_cta * pl.chain_total;
 }
 
@@ -22,6 +31,11 @@ cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const 
     const int grid = a.B * ctas_per_ds;
     const int block = chains_per_cta * 32 * W;
     const size_t smem = smem_bytes_for(a, kind, W, chains_per_cta, dtype);
+    if (kind == KIND_HMC_CC) return launch_hmc_cc(a, grid, block, smem, st);
+    if (a.grouped) {
+        if (dtype == SCCODA_F64) return launch_kernel_f64g(kind, W, a, grid, block, smem, st);
+        return launch_kernel_f32g(kind, W, a, grid, block, smem, st);
+    }
     if (dtype == SCCODA_F64) return launch_kernel_f64(kind, W, a, grid, block, smem, st);
     return launch_kernel_f32(kind, W, a, grid, block, smem, st);
 }

@@ -7,7 +7,7 @@
 
 namespace sccoda {
 
-enum { KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2 };
+enum { KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2, KIND_HMC_CC = 3 /* case/control specialisation, hmc_cc.cuh */ };
 
 }  // namespace sccoda
 
@@ -19,8 +19,21 @@ struct KArgs {
     Dims dm;
     int B, C, Umax;
     int el_smem;  // 1: stage the element list into shared memory (fp32 build, when it fits); 0: read it from global
+    int grouped;  // 1: pair / item gradient path (grouped.cuh); 0: element path (model.cuh)
+    int NImax, NOmax, NGmax, NF;
+    const int* NI;
+    const void* iy;
+    const uint16_t* ipair;
+    const uint16_t* ipos;
+    const void* pcoef;
+    const int* NG;
+    const void* oy;
+    const uint16_t* opair;
+    const uint16_t* opos;
+    const uint32_t* odesc;
     int method, num_results, num_burnin, num_adapt, num_leapfrog, max_depth;
     int step_begin, step_end, store_draws;
+    int generic_only;  // 1: never take a specialised kernel (tests compare the specialisations with the generic path)
     double step_size, target_accept;
     uint64_t seed;
     uint32_t chain_id0;
@@ -48,13 +61,21 @@ struct KArgs {
 __host__ __device__ inline size_t rnd16(size_t bytes) { return (bytes + 15) & ~size_t(15); }
 
 struct SmemPlan {
-    size_t ntot, xu, grp, rstart, colperm, el, data_total;                        // per CTA
-    size_t red, cp, rowterm, G, Gu, beta, ind, gk, vec, chain_total;       // per chain (relative)
+    size_t ntot, xu, grp, rstart, colperm, el, pcoef, iy, ipair, ipos, data_total;    // per CTA
+    size_t red, cp, rowterm, G, Gu, beta, ind, gk, vec, chain_total;                  // per chain (relative)
 };
 
-__host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int el_smem, int nvec, int W, size_t ts) {
+// counts per item of the grouped layout (SCCODA_ITEM_R of grouped.cuh / include/sccoda_b200.h)
+constexpr int kItemR = 5;
+
+// nimax > 0 selects the grouped (pair / item) layout: NP = Umax*(K+1) pair records instead of (c, psi) pairs, nf
+// result slots per pair (+ one spare) instead of the per-element G, no row terms and no column-sum scratch.
+__host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int el_smem, int nimax, int nf, int nvec,
+                                              int W, size_t ts) {
     SmemPlan p;
     const size_t NK = (size_t)N * K, UK = (size_t)Umax * K, P = (size_t)D + 2 * (size_t)D * (K - 1) + K;
+    const size_t NP = (size_t)Umax * (K + 1);
+    const bool grouped = nimax > 0;
     size_t o = 0;
     p.ntot = o; o += rnd16((size_t)N * ts);
     p.xu = o; o += rnd16((size_t)Umax * D * ts);
@@ -62,26 +83,35 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
     p.rstart = o; o += rnd16((size_t)(Umax + 1) * 4);
     p.colperm = o; o += rnd16((size_t)K * 4);
     p.el = o; o += el_smem ? rnd16(NK * 2 * ts) : 0;
+    p.pcoef = o; o += grouped ? rnd16(NP * 6 * ts) : 0;
+    p.iy = o; o += grouped ? rnd16((size_t)kItemR * nimax * ts) : 0;
+    p.ipair = o; o += grouped ? rnd16((size_t)nimax * 2) : 0;
+    p.ipos = o; o += grouped ? rnd16((size_t)nimax * 2) : 0;
     p.data_total = o;
     o = 0;
     p.red = o; o += rnd16((size_t)2 * W * 8);
-    p.cp = o; o += rnd16(UK * 2 * ts);
-    p.rowterm = o; o += rnd16((size_t)N * ts);
-    p.G = o; o += rnd16(NK * ts);
+    p.cp = o; o += grouped ? rnd16(NP * 4 * ts) : rnd16(UK * 2 * ts);
+    p.rowterm = o; o += grouped ? 0 : rnd16((size_t)N * ts);
+    p.G = o; o += grouped ? rnd16((NP * nf + 1) * ts) : rnd16(NK * ts);
     p.Gu = o; o += rnd16((size_t)Umax * ts);
     p.beta = o; o += rnd16((size_t)D * K * ts);
     p.ind = o; o += rnd16((size_t)D * (K - 1) * ts + ts);
-    p.gk = o; o += rnd16((size_t)(D + 1) * K * ts);
+    p.gk = o; o += grouped ? 0 : rnd16((size_t)(D + 1) * K * ts);
     p.vec = o; o += rnd16((size_t)nvec * rnd16(P * ts));
     p.chain_total = o;
     return p;
 }
 
 int nvec_for(int kind, int max_depth);
+// KIND_HMC -> KIND_HMC_CC when the problem has the case/control shape the specialised kernel is written for
+int select_kind(const KArgs& a, int kind, int dtype, int W);
+cudaError_t launch_hmc_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int dtype);
 cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const KArgs& a, cudaStream_t st);
 cudaError_t launch_kernel_f32(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t launch_kernel_f64(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_kernel_f32g(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_kernel_f64g(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 
 // K4 (summary.cu)
 cudaError_t launch_summary(int dtype, int B, int C, int N, int K, int D, const int* ref, int num_results, int skip,

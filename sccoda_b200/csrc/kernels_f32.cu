@@ -1,8 +1,8 @@
-// fp32 instantiation of the sampler kernels (the production arithmetic).
+// fp32 instantiation of the sampler kernels, element path (the production arithmetic).
 #include "kernels_impl.cuh"
 
 namespace sccoda {
 cudaError_t launch_kernel_f32(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
-    return launch_w<float>(kind, W, a, grid, block, smem, st);
+    return launch_w<float, false>(kind, W, a, grid, block, smem, st);
 }
 }  // namespace sccoda

@@ -13,6 +13,7 @@
 
 #include "../../include/sccoda_b200.h"
 #include "kernels.h"
+#include "grouped.cuh"
 #include "model.cuh"
 #include "philox.cuh"
 
@@ -59,6 +60,22 @@ __device__ __forceinline__ void stage_dataset(const KArgs& a, int b, const SmemP
     dt.U = a.U[b];
     dt.ref = a.ref[b];
     dt.lconst = a.lconst[b];
+    dt.pcoef = (uint32_t)pl.pcoef; dt.iy = (uint32_t)pl.iy; dt.ipair = (uint32_t)pl.ipair; dt.ipos = (uint32_t)pl.ipos;
+    dt.oy = nullptr; dt.opair = nullptr; dt.opos = nullptr; dt.odesc = nullptr;
+    dt.NI = 0; dt.NG = 0; dt.NImax = a.NImax; dt.NF = a.NF; dt.tot0 = Umax * K;
+    if (a.grouped) {
+        const int NP = Umax * (K + 1);
+        copy_to_smem(sp<T>(dt.pcoef), static_cast<const T*>(a.pcoef) + (size_t)b * NP * 6, NP * 6);
+        copy_to_smem(sp<T>(dt.iy), static_cast<const T*>(a.iy) + (size_t)b * kItemR * a.NImax, kItemR * a.NImax);
+        copy_to_smem(sp<uint16_t>(dt.ipair), a.ipair + (size_t)b * a.NImax, a.NImax);
+        copy_to_smem(sp<uint16_t>(dt.ipos), a.ipos + (size_t)b * a.NImax, a.NImax);
+        dt.oy = static_cast<const T*>(a.oy) + (size_t)b * a.NOmax;
+        dt.opair = a.opair + (size_t)b * a.NGmax;
+        dt.opos = a.opos + (size_t)b * a.NGmax;
+        dt.odesc = a.odesc + (size_t)b * a.NGmax;
+        dt.NI = a.NI[b];
+        dt.NG = a.NG[b];
+    }
 }
 
 __device__ __forceinline__ void carve_chain(uint32_t base, const SmemPlan& pl, ChainScratch& cs, uint32_t& red) {
@@ -86,22 +103,41 @@ __device__ __forceinline__ bool prologue(const KArgs& a, int nvec, DataTile<T>& 
     g.gid = threadIdx.x / TS;
     g.tid = threadIdx.x - g.gid * TS;
     c = cblk * cpc + g.gid;
-    const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem, nvec, W, sizeof(T));
+    const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem, a.grouped ? a.NImax : 0, a.NF, nvec, W,
+                                  sizeof(T));
     stage_dataset<T>(a, b, pl, dt);
     carve_chain((uint32_t)(pl.data_total + (size_t)g.gid * pl.chain_total), pl, cs, g.red);
     // the reference column of beta is identically zero (scCODA_model.py:732-734); written once
-    if (c < a.C)
+    if (c < a.C) {
         for (int d = g.tid; d < a.dm.D; d += TS) sp<T>(cs.beta)[d * a.dm.K + dt.ref] = T(0);
+        // grouped path: result slots that no item / odd group owns stay zero for the whole run
+        if (a.grouped)
+            for (int i = g.tid; i < a.Umax * (a.dm.K + 1) * a.NF + 1; i += TS) sp<T>(cs.G)[i] = T(0);
+    }
     __syncthreads();
     return c < a.C;
 }
 
 #define SCCODA_BOUNDS(W) __launch_bounds__((W) <= 4 ? 128 : 32 * (W), (W) <= 4 ? 7 : 1)
 
+// Gradient / value of the path the kernel was instantiated for (GR: grouped pair/item layout).
+template <typename T, int W, bool GR, class Epi>
+__device__ __forceinline__ void grad_of(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs, uint32_t theta_off,
+                                        const Group<W>& g, const Epi& epi) {
+    if constexpr (GR) dm_grad_items<T, W>(dm, dt, cs, theta_off, g, epi);
+    else dm_grad<T, W>(dm, dt, cs, theta_off, g, epi);
+}
+template <typename T, int W, bool GR>
+__device__ __forceinline__ double value_of(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                           uint32_t theta_off, const Group<W>& g) {
+    if constexpr (GR) return dm_value<T, W, PairRec<T>>(dm, dt, cs, theta_off, g);
+    else return dm_value<T, W, CPsi<T>>(dm, dt, cs, theta_off, g);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 unit kernel: value + gradient at given states
 // ------------------------------------------------------------------------------------------------
-template <typename T, int W>
+template <typename T, int W, bool GR>
 __global__ void SCCODA_BOUNDS(W) logp_grad_kernel(const __grid_constant__ KArgs a) {
     DataTile<T> dt;
     ChainScratch cs;
@@ -115,8 +151,8 @@ __global__ void SCCODA_BOUNDS(W) logp_grad_kernel(const __grid_constant__ KArgs 
     const T* theta_in = static_cast<const T*>(a.init) + chain * P;
     for (int i = g.tid; i < P; i += TS) sp<T>(th)[i] = theta_in[i];
     g.sync();
-    dm_grad<T, W>(a.dm, dt, cs, th, g, StoreGrad<T>{sp<T>(gr)});
-    const double lp = dm_value<T, W>(a.dm, dt, cs, th, g);
+    grad_of<T, W, GR>(a.dm, dt, cs, th, g, StoreGrad<T>{sp<T>(gr)});
+    const double lp = value_of<T, W, GR>(a.dm, dt, cs, th, g);
     T* grad_out = static_cast<T*>(a.draws) + chain * P;
     for (int i = g.tid; i < P; i += TS) grad_out[i] = sp<T>(gr)[i];
     if (g.tid == 0) a.carry[chain] = lp;
@@ -221,7 +257,7 @@ struct LeapfrogEpi {
     }
 };
 
-template <typename T, int W>
+template <typename T, int W, bool GR>
 __global__ void SCCODA_BOUNDS(W) hmc_kernel(const __grid_constant__ KArgs a) {
     DataTile<T> dt;
     ChainScratch cs;
@@ -276,12 +312,12 @@ __global__ void SCCODA_BOUNDS(W) hmc_kernel(const __grid_constant__ KArgs a) {
         for (int l = 0; l < nl; ++l) {
             const bool last = (l == nl - 1);
             LeapfrogEpi<T> epi{sp<T>(o_gw), mom, sp<T>(cur), sp<T>(nxt), last ? T(0.5) * eps : eps, eps, !boot, !last};
-            dm_grad<T, W>(a.dm, dt, cs, cur, g, epi);
+            grad_of<T, W, GR>(a.dm, dt, cs, cur, g, epi);
             if (!last) {
                 const uint32_t tmp = cur; cur = nxt; nxt = tmp;
             }
         }
-        const double lp_new = dm_value<T, W>(a.dm, dt, cs, cur, g);
+        const double lp_new = value_of<T, W, GR>(a.dm, dt, cs, cur, g);
         bool acc = true;
         double lar = 0.0;
         if (!boot) {
@@ -335,7 +371,7 @@ __device__ __forceinline__ double logaddexp_d(double x, double y) {
     return m + log(exp(x - m) + exp(y - m));
 }
 
-template <typename T, int W>
+template <typename T, int W, bool GR>
 __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
     DataTile<T> dt;
     ChainScratch cs;
@@ -427,8 +463,8 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
                     }
                 }
                 g.sync();
-                dm_grad<T, W>(a.dm, dt, cs, o_q, g, StoreGrad<T>{gq});
-                lqv = dm_value<T, W>(a.dm, dt, cs, o_q, g);
+                grad_of<T, W, GR>(a.dm, dt, cs, o_q, g, StoreGrad<T>{gq});
+                lqv = value_of<T, W, GR>(a.dm, dt, cs, o_q, g);
                 if (boot) break;
                 T kk = T(0);
 #pragma unroll 1
@@ -530,33 +566,33 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
 // ------------------------------------------------------------------------------------------------
 // launch helpers (one dtype per translation unit)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int W>
+template <typename T, int W, bool GR>
 static cudaError_t launch_one(int kind, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
     cudaError_t e;
     if (kind == KIND_LOGP) {
-        e = cudaFuncSetAttribute(logp_grad_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(logp_grad_kernel<T, W, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        logp_grad_kernel<T, W><<<grid, block, smem, st>>>(a);
+        logp_grad_kernel<T, W, GR><<<grid, block, smem, st>>>(a);
     } else if (kind == KIND_HMC) {
-        e = cudaFuncSetAttribute(hmc_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(hmc_kernel<T, W, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hmc_kernel<T, W><<<grid, block, smem, st>>>(a);
+        hmc_kernel<T, W, GR><<<grid, block, smem, st>>>(a);
     } else {
-        e = cudaFuncSetAttribute(nuts_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(nuts_kernel<T, W, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        nuts_kernel<T, W><<<grid, block, smem, st>>>(a);
+        nuts_kernel<T, W, GR><<<grid, block, smem, st>>>(a);
     }
     return cudaGetLastError();
 }
 
-template <typename T>
+template <typename T, bool GR>
 static cudaError_t launch_w(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
     switch (W) {
-        case 1: return launch_one<T, 1>(kind, a, grid, block, smem, st);
-        case 2: return launch_one<T, 2>(kind, a, grid, block, smem, st);
-        case 4: return launch_one<T, 4>(kind, a, grid, block, smem, st);
-        case 8: return launch_one<T, 8>(kind, a, grid, block, smem, st);
-        case 16: return launch_one<T, 16>(kind, a, grid, block, smem, st);
+        case 1: return launch_one<T, 1, GR>(kind, a, grid, block, smem, st);
+        case 2: return launch_one<T, 2, GR>(kind, a, grid, block, smem, st);
+        case 4: return launch_one<T, 4, GR>(kind, a, grid, block, smem, st);
+        case 8: return launch_one<T, 8, GR>(kind, a, grid, block, smem, st);
+        case 16: return launch_one<T, 16, GR>(kind, a, grid, block, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -59,6 +59,7 @@ template <typename T>
 struct alignas(2 * sizeof(T)) CPsi {
     T c;
     T psi;
+    static constexpr bool has_totals = false;
 };
 
 // One dataset (shared by all chain groups of the CTA): shared-memory offsets + global pointers.
@@ -77,13 +78,24 @@ struct DataTile {
     int U, ref;
     int nbig;              // elements [0, nbig) have counts >= 6
     double lconst;         // all theta-independent terms of the log-density (host, fp64)
+    // pair / item layout (grouped gradient path, grouped.cuh)
+    uint32_t pcoef;        // smem T[NP,6] rational coefficients of each pair
+    uint32_t iy;           // smem T[R,NImax] counts of the items
+    uint32_t ipair;        // smem uint16[NImax] pair of each item
+    uint32_t ipos;         // smem uint16[NImax] result slot of each item
+    const T* oy;           // global [NOmax] odd counts
+    const uint16_t* opair; // global [NGmax] pair / result slot / (first | count << 16) of each odd group
+    const uint16_t* opos;
+    const uint32_t* odesc;
+    int NI, NG, NImax, NF; // items / odd groups of this dataset, item stride, result slots per pair
+    int tot0;              // index of the first total pair (Umax*K)
 };
 
 // Scratch of one chain group (shared-memory byte offsets).
 struct ChainScratch {
-    uint32_t cp;       // CPsi<T>[U,K] concentrations c_uk and digamma(c_uk)
-    uint32_t rowterm;  // T[N]   digamma(S_u + n_n) - digamma(S_u)
-    uint32_t G;        // T[NK]  d logp / d log c, element-list order
+    uint32_t cp;       // CPsi<T>[U,K] concentrations c_uk and digamma(c_uk)   | grouped: PairRec<T>[Umax*(K+1)]
+    uint32_t rowterm;  // T[N]   digamma(S_u + n_n) - digamma(S_u)              | grouped: unused
+    uint32_t G;        // T[NK]  d logp / d log c, element-list order           | grouped: T[NP*NF+1] result slots
     uint32_t Gu;       // T[U]   row sums S_u of the concentrations (small-U path)
     uint32_t beta;     // T[D,K] (reference column stays 0)
     uint32_t ind;      // T[D,K-1]
@@ -472,8 +484,8 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
 // Correction of this thread's element terms for concentrations >= c_joint (rare: far tails / nearly multinomial
 // data): replaces the standard form by the joint cancellation-free form (special.cuh), which also carries the
 // -lgamma(c) that dm_value skipped for those concentrations.  Out of line: the common path keeps its small code.
-template <typename T, int W>
-__device__ __noinline__ double value_joint_fixup(const Dims& dm, const DataTile<T>& dt, const CPsi<T>* cp, T c_joint,
+template <typename T, int W, class Rec>
+__device__ __noinline__ double value_joint_fixup(const Dims& dm, const DataTile<T>& dt, const Rec* cp, T c_joint,
                                                  int tid) {
     constexpr int TS = Group<W>::SIZE;
     double fix = 0.0;
@@ -492,8 +504,9 @@ __device__ __noinline__ double value_joint_fixup(const Dims& dm, const DataTile<
 
 // Value of the log-density at theta.  Must follow dm_grad at the same theta (uses the c_uk it left in the
 // scratch).  Terms are evaluated in T, accumulated in fp64; the two O(n ln n)-sized row terms are taken in
-// fp64.  Every thread of the group receives the result.
-template <typename T, int W>
+// fp64.  Every thread of the group receives the result.  Rec = CPsi<T> (element path) or PairRec<T> (grouped path):
+// both keep the concentration of pair u*K + k in their member c.
+template <typename T, int W, class Rec>
 __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
                                         uint32_t theta_off, const Group<W>& g) {
     const int tid = g.tid;
@@ -503,7 +516,7 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     const T* boff = sigma + D;
     const T* iraw = boff + DK1;
     const T* alpha = iraw + DK1;
-    const CPsi<T>* cp = sp<CPsi<T>>(cs.cp);
+    const Rec* cp = sp<Rec>(cs.cp);
     const int* rstart = sp<int>(dt.rstart);
     const int* grp = sp<int>(dt.grp);
     const T* ntot = sp<T>(dt.ntot);
@@ -552,20 +565,25 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     }
 #pragma unroll 1
     for (int n = tid; n < dm.N; n += TS) {
-        const CPsi<T>* cu = cp + grp[n] * K;
-        // S in fp32 pairs, combined in fp64 (the conversions are the expensive part of an fp64 accumulation)
-        T S0 = T(0), S1 = T(0), S2 = T(0), S3 = T(0);
-        int k = 0;
-#pragma unroll 1
-        for (; k + 3 < K; k += 4) {
-            S0 += cu[k].c;
-            S1 += cu[k + 1].c;
-            S2 += cu[k + 2].c;
-            S3 += cu[k + 3].c;
+        if constexpr (Rec::has_totals) {
+            // grouped path: the gradient pass left S_u in the record of the total pair
+            lp += lgamma_rowdiff_f64((double)cp[dt.tot0 + grp[n]].c, (double)ntot[n]);
+        } else {
+            const Rec* cu = cp + grp[n] * K;
+            // S in fp32 pairs, combined in fp64 (the conversions are the expensive part of an fp64 accumulation)
+            T S0 = T(0), S1 = T(0), S2 = T(0), S3 = T(0);
+            int k = 0;
+    #pragma unroll 1
+            for (; k + 3 < K; k += 4) {
+                S0 += cu[k].c;
+                S1 += cu[k + 1].c;
+                S2 += cu[k + 2].c;
+                S3 += cu[k + 3].c;
+            }
+    #pragma unroll 1
+            for (; k < K; ++k) S0 += cu[k].c;
+            lp += lgamma_rowdiff_f64(((double)S0 + (double)S1) + ((double)S2 + (double)S3), (double)ntot[n]);
         }
-#pragma unroll 1
-        for (; k < K; ++k) S0 += cu[k].c;
-        lp += lgamma_rowdiff_f64(((double)S0 + (double)S1) + ((double)S2 + (double)S3), (double)ntot[n]);
     }
     // elements: lgamma(c + y) - lgamma(y); per-thread partial sums in T (<= a few dozen terms), total in fp64.
     // Concentrations >= c_joint (rare) are patched afterwards by value_joint_fixup (out of line).
@@ -593,7 +611,7 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
         }
     }
     // every thread owns a different slice of the elements in the fix-up: the flag must be uniform over the group
-    if (sizeof(T) == 4 && g.any(need_fix)) lp += value_joint_fixup<T, W>(dm, dt, cp, c_joint, tid);
+    if (sizeof(T) == 4 && g.any(need_fix)) lp += value_joint_fixup<T, W, Rec>(dm, dt, cp, c_joint, tid);
     lp = g.sum(lp) + dt.lconst;
     // HalfCauchy support: -inf as soon as one sigma_d < 0 [TFP]; every thread scans the D values (uniform)
     for (int d = 0; d < D; ++d)

@@ -41,6 +41,7 @@ class SampleOutput:
     grid: int
     smem_bytes: int
     launches: int
+    kernel_kind: int = 0   # 1 generic HMC, 2 NUTS, 3 case/control HMC (include/sccoda_b200.h: sccoda_kernel_kind)
 
     def stat(self, name: str):
         return self.stats[..., nat.STAT_NAMES.index(name)]
@@ -55,23 +56,23 @@ class DeviceProblem:
         self.C = int(chains)
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.tdtype = torch.float32 if packed.dtype == np.float32 else torch.float64
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=False)
-        self.ey, self.eycst, self.eidx = up(packed.ey), up(packed.eycst), up(packed.eidx.view(np.int32))
-        self.colperm, self.nbig = up(packed.colperm), up(packed.nbig)
-        self.ntot, self.xu = up(packed.ntot), up(packed.xu)
-        self.grp, self.rstart, self.U, self.ref = up(packed.grp), up(packed.rstart), up(packed.U), up(packed.ref)
-        self.lconst = up(packed.lconst)
         self.B, self.N, self.K, self.D, self.P = packed.B, packed.N, packed.K, packed.D, packed.P
-        self.c_problem = nat.Problem(
-            B=self.B, C=self.C, N=self.N, K=self.K, D=self.D, Umax=packed.Umax,
-            dtype=nat.F32 if packed.dtype == np.float32 else nat.F64, nbig_min=packed.nbig_min,
-            ey=_ptr(self.ey), eycst=_ptr(self.eycst), eidx=_ptr(self.eidx), colperm=_ptr(self.colperm),
-            nbig=_ptr(self.nbig), ntot=_ptr(self.ntot), xu=_ptr(self.xu), grp=_ptr(self.grp),
-            rstart=_ptr(self.rstart), U=_ptr(self.U), ref=_ptr(self.ref), lconst=_ptr(self.lconst))
+        # device copies of every array of the packed layout (unsigned integer arrays travel as same-width signed views)
+        signed = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32}
+        self._dev = {}
+
+        def ptr(name):
+            a = np.ascontiguousarray(getattr(packed, name))
+            if a.dtype in signed:
+                a = a.view(signed[a.dtype])
+            self._dev[name] = torch.from_numpy(a).to(self.device, non_blocking=False)
+            return self._dev[name].data_ptr()
+
+        self.c_problem = nat.Problem(C=self.C, **nat.problem_fields(packed, ptr))
 
     @classmethod
-    def from_arrays(cls, x, y, ref, chains: int, dtype=np.float32, device: Optional[int] = None):
-        return cls(pack(x, y, ref, dtype=dtype), chains, device)
+    def from_arrays(cls, x, y, ref, chains: int, dtype=np.float32, device: Optional[int] = None, grouped=None):
+        return cls(pack(x, y, ref, dtype=dtype, grouped=grouped), chains, device)
 
     # ------------------------------------------------------------------ K1
     def logp_grad(self, theta):
@@ -91,13 +92,14 @@ class DeviceProblem:
     def make_sampler(self, method: int, num_results: int, num_burnin: int, num_adapt: Optional[int] = None,
                      num_leapfrog: int = 10, max_tree_depth: int = 10, step_size: float = 0.01,
                      target_accept: float = 0.75, seed: int = 0, chain_id0: int = 0,
-                     warps_per_chain: int = 0, chains_per_cta: int = 0) -> nat.Sampler:
+                     warps_per_chain: int = 0, chains_per_cta: int = 0, generic_only: bool = False) -> nat.Sampler:
         if num_adapt is None:
             num_adapt = int(0.8 * num_burnin)            # scCODA_model.py:284-285
         return nat.Sampler(method=method, num_results=num_results, num_burnin=num_burnin, num_adapt=num_adapt,
                            num_leapfrog=num_leapfrog, max_tree_depth=max_tree_depth, step_begin=0, step_end=0,
                            step_size=step_size, target_accept=target_accept, seed=seed, chain_id0=chain_id0,
-                           warps_per_chain=warps_per_chain, store_draws=1, chains_per_cta=chains_per_cta)
+                           warps_per_chain=warps_per_chain, store_draws=1, chains_per_cta=chains_per_cta,
+                           generic_only=int(bool(generic_only)))
 
     def plan(self, smp: nat.Sampler):
         w, c, g, s = (ctypes.c_int32() for _ in range(4))
@@ -120,6 +122,9 @@ class DeviceProblem:
         total = smp.num_burnin + smp.num_results
         chunk = total if not chunk else int(chunk)
         w, cpc, grid, smem = self.plan(smp)
+        kind = ctypes.c_int32()
+        nat.check(nat.lib().sccoda_kernel_kind(ctypes.byref(self.c_problem), ctypes.byref(smp), ctypes.byref(kind)),
+                  "sccoda_kernel_kind")
         launches = 0
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream()
@@ -142,7 +147,7 @@ class DeviceProblem:
             ms = e0.elapsed_time(e1)
         smp.step_begin, smp.step_end = 0, 0
         return SampleOutput(draws=draws, stats=stats, carry=carry, kernel_ms=ms, warps_per_chain=w,
-                            chains_per_cta=cpc, grid=grid, smem_bytes=smem, launches=launches)
+                            chains_per_cta=cpc, grid=grid, smem_bytes=smem, launches=launches, kernel_kind=kind.value)
 
     # ------------------------------------------------------------------ K4
     def summary_width(self) -> int:
@@ -181,13 +186,7 @@ def sample_host(packed: PackedProblem, chains: int, init: np.ndarray, smp: nat.S
     B, C, S, P = packed.B, int(chains), smp.num_results, packed.P
     init = np.ascontiguousarray(init, dtype=dt)
     assert init.shape == (B, C, P)
-    prob = nat.Problem(B=B, C=C, N=packed.N, K=packed.K, D=packed.D, Umax=packed.Umax,
-                       dtype=nat.F32 if dt == np.float32 else nat.F64, nbig_min=packed.nbig_min,
-                       ey=packed.ey.ctypes.data, eycst=packed.eycst.ctypes.data, eidx=packed.eidx.ctypes.data,
-                       colperm=packed.colperm.ctypes.data, nbig=packed.nbig.ctypes.data,
-                       ntot=packed.ntot.ctypes.data,
-                       xu=packed.xu.ctypes.data, grp=packed.grp.ctypes.data, rstart=packed.rstart.ctypes.data,
-                       U=packed.U.ctypes.data, ref=packed.ref.ctypes.data, lconst=packed.lconst.ctypes.data)
+    prob = nat.Problem(C=C, **nat.problem_fields(packed, lambda name: getattr(packed, name).ctypes.data))
     draws = np.empty((B, C, S, P), dtype=dt) if want_draws else None
     stats = np.empty((B, C, S, nat.NSTAT), dtype=dt) if want_draws else None
     width = nat.NSUM_PARAM * P + nat.NSUM_BETA * packed.D * packed.K + nat.NSUM_SCALAR

@@ -29,12 +29,13 @@ def _oracle_run(x, y, ref, init, method, nr, nb, **kw):
 
 @pytest.mark.parametrize("method,steps,tol", [(0, 40, 1e-9), (1, 8, 1e-7), (2, 6, 1e-6)])
 @pytest.mark.parametrize("W", [1, 2, 4])
-def test_fp64_trajectory_follows_oracle(method, steps, tol, W):
+@pytest.mark.parametrize("grouped", [False, True])
+def test_fp64_trajectory_follows_oracle(method, steps, tol, W, grouped):
     from sccoda_b200.engine import DeviceProblem
     x, y, _ = haber_salm()
     init = _init(np.random.RandomState(0), 1, 8, 3)
     d_ref, s_ref = _oracle_run(x, y, 5, init, method, steps, 0, num_adapt=steps, seed=7, chain_id0=3)
-    prob = DeviceProblem.from_arrays(x, y, 5, chains=3, dtype=np.float64)
+    prob = DeviceProblem.from_arrays(x, y, 5, chains=3, dtype=np.float64, grouped=grouped)
     smp = prob.make_sampler(method, steps, 0, num_adapt=steps, seed=7, chain_id0=3, warps_per_chain=W)
     out = prob.sample(init[None], smp)
     d = out.draws.cpu().numpy()
@@ -47,14 +48,15 @@ def test_fp64_trajectory_follows_oracle(method, steps, tol, W):
     assert np.allclose(out.stat("log_accept_ratio").cpu().numpy()[fin], s_ref["log_accept_ratio"][fin], atol=1e-6)
 
 
-def test_fp64_trajectory_synthetic_multi_covariate():
+@pytest.mark.parametrize("grouped", [False, True])
+def test_fp64_trajectory_synthetic_multi_covariate(grouped):
     """D=3 covariates (U=8 groups after packing), K=9: exercises the grouped layout against the plain oracle."""
     from sccoda_b200.engine import DeviceProblem
     x, y = synthetic_dataset(5, N=12, K=9, D=3)
     y[0, 0] = 0
     init = _init(np.random.RandomState(1), 3, 9, 2)
     d_ref, s_ref = _oracle_run(x, y, 2, init, 0, 30, 10, num_adapt=30, seed=5, chain_id0=0)
-    prob = DeviceProblem.from_arrays(x, y, 2, chains=2, dtype=np.float64)
+    prob = DeviceProblem.from_arrays(x, y, 2, chains=2, dtype=np.float64, grouped=grouped)
     out = prob.sample(init[None], prob.make_sampler(0, 30, 10, num_adapt=30, seed=5))
     assert np.abs(out.draws.cpu().numpy() - d_ref).max() < 1e-8
 
@@ -86,8 +88,10 @@ def test_chain_streams_are_independent_of_sharding():
 
 
 @pytest.mark.parametrize("method", [0, 1])
-def test_fp32_statistical_parity_haber(method):
-    """64 fp32 device chains vs 64 fp64 oracle chains on Haber/Salmonella, sample_hmc(_da) semantics.
+@pytest.mark.parametrize("variant", ["generic", "grouped", "case_control"])
+def test_fp32_statistical_parity_haber(method, variant):
+    """64 fp32 device chains vs 64 fp64 oracle chains on Haber/Salmonella, sample_hmc(_da) semantics, for the
+    element path, the pair/item path and the case/control kernel (one warp per chain, state in registers).
 
     Tolerances are Monte-Carlo tolerances: means over 64 chains; per-chain sd taken from the oracle sample."""
     from sccoda_b200.engine import DeviceProblem
@@ -95,8 +99,11 @@ def test_fp32_statistical_parity_haber(method):
     C, nr, nb = 64, 3000, 1500
     init = _init(np.random.RandomState(7), 1, 8, C)
     d_ref, s_ref = _oracle_run(x, y, 5, init, method, nr, nb, seed=21, chain_id0=0)
-    prob = DeviceProblem.from_arrays(x, y, 5, chains=C, dtype=np.float32)
-    out = prob.sample(init[None], prob.make_sampler(method, nr, nb, seed=22))
+    prob = DeviceProblem.from_arrays(x, y, 5, chains=C, dtype=np.float32, grouped=variant != "generic")
+    smp = prob.make_sampler(method, nr, nb, seed=22, warps_per_chain=1 if variant == "case_control" else 0,
+                            generic_only=variant != "case_control")
+    out = prob.sample(init[None], smp)
+    assert out.kernel_kind == (3 if variant == "case_control" else 1)
     d = out.draws.double().cpu().numpy()
     assert np.isfinite(d).all()
 
@@ -124,6 +131,41 @@ def test_fp32_statistical_parity_haber(method):
     se = np.hypot(inc.std(0, ddof=1), inc_r.std(0, ddof=1)) / np.sqrt(C)
     assert np.all(np.abs(inc.mean(0) - inc_r.mean(0)) < 5 * se + 0.03), (inc.mean(0), inc_r.mean(0))
     assert inc.mean(0)[1] > 0.9                              # Enterocyte is credible in every tutorial run
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_case_control_kernel_follows_generic_kernel(method):
+    """Same Philox streams, same arithmetic per parameter: the register-resident case/control kernel and the generic
+    kernel agree step by step in fp32 until rounding differences of the summation orders are amplified."""
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    B, C, K = 3, 4, 20
+    xs, ys = zip(*[synthetic_dataset(40 + b, N=20, K=K) for b in range(B)])
+    ys = np.stack(ys)
+    ys[1, 3, 2] = 0                                              # one dataset with a pseudocount (odd group)
+    init = _init(np.random.RandomState(11), 1, K, B * C).reshape(B, C, -1)
+    prob = DeviceProblem(pack(np.stack(xs), ys, np.array([19, 0, 7]), dtype=np.float32), chains=C)
+    assert prob.packed.grouped == 1 and prob.packed.NF <= 4
+    outs = []
+    for generic_only in (True, False):
+        smp = prob.make_sampler(method, 16, 0, num_adapt=16, seed=3, warps_per_chain=1, generic_only=generic_only)
+        outs.append(prob.sample(init, smp))
+    assert outs[0].kernel_kind == 1 and outs[1].kernel_kind == 3
+    d0, d1 = outs[0].draws.cpu().numpy(), outs[1].draws.cpu().numpy()
+    assert np.isfinite(d1).all()
+    # dual averaging jumps to 10x the initial step size at once: its trajectories are chaotic after a few steps
+    n = 8 if method == 0 else 2
+    assert np.abs(d0[:, :, :n] - d1[:, :, :n]).max() < 2e-3
+    assert np.array_equal(outs[0].stat("is_accepted").cpu().numpy()[:, :, :n],
+                          outs[1].stat("is_accepted").cpu().numpy()[:, :, :n])
+    assert np.allclose(outs[0].stat("target_log_prob").cpu().numpy()[:, :, :n],
+                       outs[1].stat("target_log_prob").cpu().numpy()[:, :, :n], atol=5e-2)
+    assert np.allclose(outs[0].stat("step_size").cpu().numpy()[:, :, :n],
+                       outs[1].stat("step_size").cpu().numpy()[:, :, :n], rtol=1e-3)
+    # chunked resume of the case/control kernel is bit-identical to the single launch
+    smp = prob.make_sampler(method, 16, 0, num_adapt=16, seed=3, warps_per_chain=1)
+    many = prob.sample(init, smp, chunk=5)
+    assert many.launches > 1 and np.array_equal(many.draws.cpu().numpy(), d1)
 
 
 def test_fp32_statistical_parity_nuts():

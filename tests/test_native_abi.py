@@ -41,18 +41,13 @@ def test_header_constants_match_binding():
 
 
 def _problem(pk, C):
-    return nat.Problem(B=pk.B, C=C, N=pk.N, K=pk.K, D=pk.D, Umax=pk.Umax, dtype=nat.F32, nbig_min=pk.nbig_min,
-                       ey=pk.ey.ctypes.data, eycst=pk.eycst.ctypes.data, eidx=pk.eidx.ctypes.data,
-                       colperm=pk.colperm.ctypes.data, nbig=pk.nbig.ctypes.data,
-                       ntot=pk.ntot.ctypes.data, xu=pk.xu.ctypes.data,
-                       grp=pk.grp.ctypes.data, rstart=pk.rstart.ctypes.data, U=pk.U.ctypes.data,
-                       ref=pk.ref.ctypes.data, lconst=pk.lconst.ctypes.data)
+    return nat.Problem(C=C, **nat.problem_fields(pk, lambda name: getattr(pk, name).ctypes.data))
 
 
 def _sampler(**kw):
     d = dict(method=0, num_results=100, num_burnin=50, num_adapt=40, num_leapfrog=10, max_tree_depth=10, step_begin=0,
              step_end=0, step_size=0.01, target_accept=0.75, seed=1, chain_id0=0, warps_per_chain=0, store_draws=1,
-             chains_per_cta=0)
+             chains_per_cta=0, generic_only=0)
     d.update(kw)
     return nat.Sampler(**d)
 
@@ -104,6 +99,27 @@ def test_problem_validation():
     p = _problem(pk, 4)
     p.ey = None
     assert _plan(p, _sampler())[0] == -7
+    assert pk.grouped == 1
+    p = _problem(pk, 4)
+    p.pcoef = None
+    assert _plan(p, _sampler())[0] == -7
+    p = _problem(pk, 4)
+    p.NImax = 7                       # must be even
+    assert _plan(p, _sampler())[0] == -6
+
+
+def test_problem_struct_matches_header():
+    """Field order of the ctypes mirror == field order of `struct sccoda_problem` in the header."""
+    src = open(os.path.join(ROOT, "include", "sccoda_b200.h")).read()
+    body = re.search(r"typedef struct sccoda_problem \{(.*?)\} sccoda_problem;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip().lstrip("*") for n in decl.split(",")]
+            names[-len(decl.split(",")):] = [re.split(r"[\s\*]+", n.strip())[-1] for n in decl.split(",")]
+    assert names == [f[0] for f in nat.Problem._fields_], names
 
 
 def test_check_raises_runtime_error():

@@ -85,3 +85,75 @@ def test_batched_shapes_and_errors():
         pack(np.zeros((4, 1)), np.ones((5, 3)), 0)
     with pytest.raises(NameError):
         pack(np.zeros((5, 1)), np.ones((5, 3)), 3)
+
+
+def _direct_bracket(vals, c):
+    from scipy.special import digamma
+    return sum(digamma(c + v) - digamma(c) for v in vals)
+
+
+def _layout_bracket(pk, b, p, c):
+    """Br_p evaluated from the pair / item layout exactly as csrc/grouped.cuh does (scipy fp64)."""
+    from scipy.special import digamma
+    from sccoda_b200._pack import ITEM_R
+    slots = np.zeros(pk.NP * pk.NF + 1)
+    for i in range(pk.NI[b]):
+        if pk.ipair[b, i] == p:
+            assert pk.ipos[b, i] // pk.NF == p and slots[pk.ipos[b, i]] == 0.0
+            slots[pk.ipos[b, i]] = sum(digamma(c + pk.iy[b, j, i]) - digamma(c + 6.0) for j in range(ITEM_R))
+    for q in range(pk.NG[b]):
+        if pk.opair[b, q] == p:
+            o0, no = int(pk.odesc[b, q]) & 0xffff, int(pk.odesc[b, q]) >> 16
+            assert pk.opos[b, q] // pk.NF == p and slots[pk.opos[b, q]] == 0.0 and no > 0
+            slots[pk.opos[b, q]] = sum(digamma(c + pk.oy[b, t]) - digamma(c + 6.0) for t in range(o0, o0 + no))
+    a = c * (c + 5.0)
+    co = pk.pcoef[b, p]
+    return (co[0] * c + co[1]) / a + (co[2] * c + co[3]) / (a + 4.0) + (co[4] * c + co[5]) / (a + 6.0) \
+        + slots[p * pk.NF:(p + 1) * pk.NF].sum()
+
+
+@pytest.mark.parametrize("shape", [(12, 7, 1), (6, 8, 1), (30, 5, 2)])
+def test_pair_item_layout_reproduces_brackets(shape):
+    """sum_n [psi(c + y_n) - psi(c)] of every pair (cell types and row totals) from items + rational + odd counts."""
+    N, K, D = shape
+    x, y = synthetic_dataset(3, N=N, K=K, D=D)
+    y[0, 0] = 0                 # pseudocount 0.5 -> odd count
+    y[1, 1] = 3
+    y[2, 2] = 1
+    y[3, 3] = 5
+    y[4, 4] = 2.5               # non-integer data -> odd count
+    y[5, 1] = 4
+    pk = pack(x, y, K - 1, dtype=np.float64, grouped=True)
+    assert pk.grouped == 1 and pk.NImax % 2 == 0 and pk.NImax >= pk.NI[0]
+    assert pk.iy.shape == (1, 5, pk.NImax) and pk.ipair.dtype == np.uint16 and pk.odesc.dtype == np.uint32
+    assert np.all(pk.iy >= 6.0) and pk.NF >= 2 and pk.NF & (pk.NF - 1) == 0
+    n_odd = int((pk.odesc[0, :pk.NG[0]] >> 16).sum())
+    assert 2.5 in pk.oy[0, :n_odd] and 0.5 in pk.oy[0, :n_odd]
+    rs = np.random.RandomState(1)
+    U, Umax = int(pk.U[0]), pk.Umax
+    for u in range(U):
+        rows = range(pk.rstart[0, u], pk.rstart[0, u + 1])
+        for k in range(K + 1):
+            p = u * K + k if k < K else Umax * K + u
+            vals = [pk.y[0, n, k] if k < K else pk.ntot[0, n] for n in rows]
+            for c in (np.exp(rs.randn()), 1e-3, 250.0):
+                ref = _direct_bracket(vals, c)
+                assert abs(_layout_bracket(pk, 0, p, c) - ref) <= 1e-12 * max(1.0, abs(ref))
+
+
+def test_pair_item_layout_auto_mode():
+    """Few covariate groups -> grouped gradient path; one row per group (continuous covariate) -> element path."""
+    x, y = synthetic_dataset(0)
+    assert pack(x, y, 19).grouped == 1
+    rs = np.random.RandomState(0)
+    assert pack(x + rs.randn(*x.shape), y, 19).grouped == 0
+    assert pack(x + rs.randn(*x.shape), y, 19, grouped=True).grouped == 1
+    # items of a batch are padded to a common even count; unused item slots are harmless (count 6, pair 0)
+    xs, ys = zip(*[synthetic_dataset(s) for s in range(4)])
+    ys = np.stack(ys)
+    ys[1, :, 3] = 2
+    pk = pack(np.stack(xs), ys, 19)
+    assert pk.NI.min() < pk.NI.max() <= pk.NImax
+    b = int(np.argmin(pk.NI))
+    assert np.all(pk.iy[b, :, pk.NI[b]:] == 6.0) and np.all(pk.ipair[b, pk.NI[b]:] == 0)
+    assert np.all(pk.ipos[b, pk.NI[b]:] == pk.NP * pk.NF)            # padding items write to the spare slot

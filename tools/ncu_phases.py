@@ -13,11 +13,20 @@ import sys
 
 # (file, first line, last line, label) — edit when the sources move
 PHASES = [
-    ("model.cuh", 167, 180, "F1 effects"),
-    ("model.cuh", 181, 243, "F2/F3 concentrations, row terms"),
-    ("model.cuh", 245, 300, "E elements"),
-    ("model.cuh", 302, 455, "B column sums + chain rule + epilogue"),
-    ("model.cuh", 456, 600, "value"),
+    ("hmc_cc.cuh", 56, 59, "cc: effects"),
+    ("hmc_cc.cuh", 60, 73, "cc: pair records + totals"),
+    ("hmc_cc.cuh", 74, 96, "cc: items"),
+    ("hmc_cc.cuh", 97, 112, "cc: brackets + chain rule"),
+    ("hmc_cc.cuh", 113, 400, "cc: sampler (momentum, leapfrog, accept, adapt, trace)"),
+    ("grouped.cuh", 130, 169, "P0 effects (grouped)"),
+    ("grouped.cuh", 170, 216, "P1 pair records + totals (grouped)"),
+    ("grouped.cuh", 217, 239, "E items (grouped)"),
+    ("grouped.cuh", 240, 320, "C columns + chain rule + epilogue (grouped)"),
+    ("model.cuh", 167, 203, "F1 effects"),
+    ("model.cuh", 204, 266, "F2/F3 concentrations, row terms"),
+    ("model.cuh", 267, 323, "E elements"),
+    ("model.cuh", 324, 478, "B column sums + chain rule + epilogue"),
+    ("model.cuh", 479, 640, "value"),
     ("kernels_impl.cuh", 0, 100000, "sampler (momentum, accept, adapt, trace)"),
 ]
 

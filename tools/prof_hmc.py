@@ -26,15 +26,17 @@ ap.add_argument("--W", type=int, default=0)
 ap.add_argument("--cpc", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--step-size", type=float, default=0.02)
+ap.add_argument("--generic", type=int, default=0, help="1: never take the case/control kernel")
+ap.add_argument("--grouped", type=int, default=-1, help="-1 auto, 0 element path, 1 pair/item path")
 a = ap.parse_args()
 
 x, y, _ = generate_sweep(a.datasets, K=a.K, n_per_group=a.n_per_group)
-pk = pack(x, y, a.K - 1, dtype=np.float32)
+pk = pack(x, y, a.K - 1, dtype=np.float32, grouped=None if a.grouped < 0 else bool(a.grouped))
 init = sch.initial_states(a.datasets, a.chains, 1, a.K, seed=1).astype(np.float32)
 prob = DeviceProblem(pk, chains=a.chains)
-smp = prob.make_sampler(a.method, a.results, a.burnin, step_size=a.step_size, seed=3, warps_per_chain=a.W, chains_per_cta=a.cpc)
+smp = prob.make_sampler(a.method, a.results, a.burnin, step_size=a.step_size, seed=3, warps_per_chain=a.W, chains_per_cta=a.cpc, generic_only=bool(a.generic))
 for _ in range(a.reps):
     out = prob.sample(init, smp)
 ge = a.datasets * a.chains * (a.results + a.burnin) * 10
-print(f"W={out.warps_per_chain} cpc={out.chains_per_cta} grid={out.grid} smem={out.smem_bytes} ms={out.kernel_ms:.3f} "
+print(f"grouped={pk.grouped} kind={out.kernel_kind} W={out.warps_per_chain} cpc={out.chains_per_cta} grid={out.grid} smem={out.smem_bytes} ms={out.kernel_ms:.3f} "
       f"grad-evals/s={ge / out.kernel_ms * 1e3:.4e} acc={out.stat('is_accepted').mean().item():.3f}")
