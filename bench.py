@@ -191,7 +191,8 @@ class ClockSampler:
                 "power_w_max": float(max(power)) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-PACKED_DEVICE_FIELDS = ("ey", "eycst", "eidx", "colperm", "nbig", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst")
+PACKED_DEVICE_FIELDS = ("ey", "eycst", "eidx", "colperm", "nbig", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst",
+                        "NI", "iy", "ipair", "ipos", "pcoef", "NG", "oy", "opair", "opos", "odesc")
 
 
 def measured_peaks():
@@ -209,9 +210,11 @@ def pinned_copy(packed):
     keep = []
 
     def pin(arr):
-        t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        arr = np.ascontiguousarray(arr)
+        signed = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32}.get(arr.dtype)
+        t = torch.from_numpy(arr.view(signed) if signed else arr).pin_memory()
         keep.append(t)
-        return t.numpy()
+        return t.numpy().view(arr.dtype)
     fields = {f.name: getattr(packed, f.name) for f in dataclasses.fields(packed)}
     for k in PACKED_DEVICE_FIELDS:
         fields[k] = pin(fields[k])

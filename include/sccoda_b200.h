@@ -105,6 +105,7 @@ typedef struct sccoda_problem {
     int32_t grouped;       /* 1: gradient by pairs / items (few covariate groups); 0: by single counts */
     int32_t NImax, NOmax;  /* item / odd-count slots per dataset (grouped layout; 0 when unused) */
     int32_t NGmax, NF;     /* odd-group slots per dataset; result slots per pair (power of two >= 2) */
+    int32_t NT, NOT;       /* largest number of items / of odd counts of one pair (over all datasets) */
     int32_t reserved0;
     const void* ey;
     const void* eycst;
@@ -172,7 +173,7 @@ int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, in
                        int32_t* chains_per_cta, int32_t* grid, int32_t* smem_bytes);
 
 /* Which kernel sccoda_sample would launch: 1 = generic HMC, 2 = NUTS, 3 = case/control HMC specialisation
- * (D == 1, <= 2 covariate groups, K <= 32, NF <= 4, fp32, one warp per chain, grouped layout). */
+ * (D == 1, Umax == 2 covariate groups, K <= 31, fp32, one warp per chain, grouped layout). */
 int sccoda_kernel_kind(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* kind);
 
 /* Host-buffer convenience (the end-to-end path): all pointers are HOST memory; copies in, runs on `device`,

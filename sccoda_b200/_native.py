@@ -29,7 +29,8 @@ class Problem(ctypes.Structure):
                 ("D", ctypes.c_int32), ("Umax", ctypes.c_int32), ("dtype", ctypes.c_int32),
                 ("nbig_min", ctypes.c_int32),
                 ("grouped", ctypes.c_int32), ("NImax", ctypes.c_int32), ("NOmax", ctypes.c_int32),
-                ("NGmax", ctypes.c_int32), ("NF", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+                ("NGmax", ctypes.c_int32), ("NF", ctypes.c_int32), ("NT", ctypes.c_int32), ("NOT", ctypes.c_int32),
+                ("reserved0", ctypes.c_int32),
                 ("ey", ctypes.c_void_p), ("eycst", ctypes.c_void_p), ("eidx", ctypes.c_void_p),
                 ("colperm", ctypes.c_void_p), ("nbig", ctypes.c_void_p),
                 ("ntot", ctypes.c_void_p), ("xu", ctypes.c_void_p),
@@ -46,7 +47,7 @@ def problem_fields(pk, ptr):
     names = ("ey", "eycst", "eidx", "colperm", "nbig", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst",
              "NI", "iy", "ipair", "ipos", "pcoef", "NG", "oy", "opair", "opos", "odesc")
     kw = dict(B=pk.B, N=pk.N, K=pk.K, D=pk.D, Umax=pk.Umax, dtype=F32 if pk.dtype.itemsize == 4 else F64,
-              nbig_min=pk.nbig_min, grouped=pk.grouped, NImax=pk.NImax, NOmax=pk.NOmax, NGmax=pk.NGmax, NF=pk.NF)
+              nbig_min=pk.nbig_min, grouped=pk.grouped, NImax=pk.NImax, NOmax=pk.NOmax, NGmax=pk.NGmax, NF=pk.NF, NT=pk.NT, NOT=pk.NOT)
     kw.update({n: ptr(n) for n in names})
     return kw
 

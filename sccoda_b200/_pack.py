@@ -50,6 +50,8 @@ class PackedProblem:
     NOmax: int = 0                   # odd-count slots per dataset (>= 1)
     NGmax: int = 0                   # odd-group slots per dataset (>= 1)
     NF: int = 0                      # result slots per pair (power of two >= 2): its items + its odd group
+    NT: int = 0                      # largest number of items of one pair
+    NOT: int = 0                     # largest number of odd counts of one pair
     NI: np.ndarray = None            # [B] int32 items of dataset b
     NG: np.ndarray = None            # [B] int32 odd groups of dataset b
     iy: np.ndarray = None            # [B,ITEM_R,NImax] counts >= 6 of each item, padded with 6
@@ -104,6 +106,7 @@ def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndar
     pcoef = np.zeros((B, NP, 6))
     per_ds = []
     nslot_max = 1
+    nt_max, not_max = 1, 0
     for b in range(B):
         yb, pb, tb, ob, opb, otb, odb = [], [], [], [], [], [], []
         n_odd = 0
@@ -120,6 +123,7 @@ def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndar
                                        W[:, 2] + W[:, 3], 3.0 * W[:, 2] + 2.0 * W[:, 3]], axis=1)
             nf = -(-nb // R)
             nslot_max = max(nslot_max, int((nf + (no > 0)).max()))
+            nt_max, not_max = max(nt_max, int(nf.max())), max(not_max, int(no.max()))
             # columns sorted by decreasing count: the big ones come first, everything else becomes padding
             srt = -np.sort(-np.where(big, blk, 6.0), axis=0)
             depth = int(nf.max()) * R
@@ -171,7 +175,7 @@ def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndar
         opair[b, :NG[b]] = opb
         opos[b, :NG[b]] = opb * NF + otb
         odesc[b, :NG[b]] = odb
-    return dict(NF=NF, NImax=NImax, NOmax=NOmax, NGmax=NGmax, NI=NI, NG=NG, iy=iy, ipair=ipair, ipos=ipos, pcoef=pcoef,
+    return dict(NT=nt_max, NOT=not_max, NF=NF, NImax=NImax, NOmax=NOmax, NGmax=NGmax, NI=NI, NG=NG, iy=iy, ipair=ipair, ipos=ipos, pcoef=pcoef,
                 oy=oy, opair=opair, opos=opos, odesc=odesc)
 
 
@@ -250,7 +254,7 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
     if grouped is None:
         grouped = bool(ITEM_R * int(it["NI"].max()) <= 1.6 * N * (K + 1))
     return PackedProblem(grouped=int(bool(grouped)), NImax=it["NImax"], NOmax=it["NOmax"], NGmax=it["NGmax"],
-                         NF=it["NF"], NI=it["NI"], NG=it["NG"], iy=np.ascontiguousarray(it["iy"], dtype),
+                         NF=it["NF"], NT=it["NT"], NOT=it["NOT"], NI=it["NI"], NG=it["NG"], iy=np.ascontiguousarray(it["iy"], dtype),
                          ipair=it["ipair"], ipos=it["ipos"], pcoef=np.ascontiguousarray(it["pcoef"], dtype),
                          oy=np.ascontiguousarray(it["oy"], dtype), opair=it["opair"], opos=it["opos"],
                          odesc=it["odesc"],

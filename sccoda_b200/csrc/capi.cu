@@ -57,6 +57,7 @@ int validate(const sccoda_problem* p) {
         if (p->NImax < 2 || (p->NImax & 1) || p->NImax > 65535 || p->NOmax < 1 || p->NOmax > 65535 || p->NGmax < 1)
             return fail(-6, "grouped layout needs an even 2 <= NImax <= 65535, 1 <= NOmax <= 65535 and NGmax >= 1 (got %d, %d, %d)",
                         p->NImax, p->NOmax, p->NGmax);
+        if (p->NT < 1 || p->NT > p->NF || p->NOT < 0) return fail(-6, "grouped layout needs 1 <= NT <= NF and NOT >= 0 (got %d, %d)", p->NT, p->NOT);
         if (p->NF < 2 || (p->NF & (p->NF - 1))) return fail(-6, "grouped layout needs NF = power of two >= 2 (got %d)", p->NF);
         if ((uint64_t)p->Umax * (p->K + 1) * p->NF > 65535ull) return fail(-6, "grouped layout needs Umax*(K+1)*NF <= 65535");
         if (!p->NI || !p->iy || !p->ipair || !p->ipos || !p->pcoef || !p->NG || !p->oy || !p->opair || !p->opos || !p->odesc)
@@ -78,6 +79,7 @@ void fill_dims(const sccoda_problem* p, sccoda::KArgs& a) {
     a.grouped = p->grouped ? 1 : 0;
     a.NImax = a.grouped ? p->NImax : 0; a.NOmax = a.grouped ? p->NOmax : 0;
     a.NGmax = a.grouped ? p->NGmax : 0; a.NF = a.grouped ? p->NF : 0;
+    a.NT = a.grouped ? p->NT : 0; a.NOT = a.grouped ? p->NOT : 0;
     a.NI = p->NI; a.iy = p->iy; a.ipair = p->ipair; a.ipos = p->ipos; a.pcoef = p->pcoef;
     a.NG = p->NG; a.oy = p->oy; a.opair = p->opair; a.opos = p->opos; a.odesc = p->odesc;
 }

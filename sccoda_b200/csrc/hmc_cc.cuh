@@ -1,17 +1,85 @@
 // K2cc — HMC for case/control designs, the shape scCODA is mostly run on and the one the benchmark sweep uses:
-// one covariate (D == 1), two covariate groups (U <= 2), K <= 32 cell types, fp32, one warp per chain.
+// one covariate (D == 1), two covariate groups (Umax == 2), K <= 31 cell types, fp32, one warp per chain.
 //
 // Same algorithm, same Philox streams and same arithmetic per parameter as hmc_kernel (kernels_impl.cuh, which
 // follows sccoda/model/scCODA_model.py:276-315, :382-424 and the TFP semantics of SURVEY §8c); what changes is
-// where things live.  Lane k owns cell type k for the whole run: alpha_k, b_offset_k, ind_raw_k, their momenta
-// and gradients are REGISTERS (sigma_d and its momentum are replicated in every lane), so the leapfrog update is
-// a handful of FFMAs without shared-memory traffic, the spike-and-slab effect, both concentrations and both
-// pair records of the cell type never leave the lane, and the chain rule needs one warp reduction (sigma_d).
-// Shared memory holds the staged dataset, the pair records the item pass reads, and the item results.
+// where things live.  Lane k owns cell type k for the whole run — lane K owns the row totals, which enter the
+// Dirichlet-multinomial exactly like one more cell type with concentration S_u = sum_k c_uk — and everything a
+// lane owns comes in twos (the two covariate groups), so it is evaluated on packed fp32 pairs (FFMA2):
+//   * alpha_k, b_offset_k, ind_raw_k, their momenta and gradients are REGISTERS (sigma_d is replicated in every
+//     lane): the leapfrog update is a handful of FFMAs without shared-memory traffic;
+//   * the spike-and-slab effect, both concentrations, both pair records (grouped.cuh), the items of both pairs and
+//     both brackets never leave the lane: the gradient needs no shared-memory round trip and no barrier, only
+//     warp shuffles (S_u, the brackets of the totals, sigma_d);
+//   * shared memory holds the staged dataset at compile-time offsets (lane-major, conflict-free) and, for the
+//     value pass, the concentrations.
 #pragma once
 #include "kernels_impl.cuh"
 
 namespace sccoda {
+
+// ------------------------------------------------------------------------------------------------
+// Packed fp32 arithmetic: Blackwell issues two FMAs per instruction on 64-bit register pairs (FFMA2 / fma.rn.f32x2).
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 dup2(float v) { return pk2(v, v); }
+__device__ __forceinline__ float lo2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float hi2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 rcp2(f32x2 v) { return pk2(rcp_fast(lo2(v)), rcp_fast(hi2(v))); }
+__device__ __forceinline__ f32x2 lg2_2(f32x2 v) { return pk2(lg2_fast(lo2(v)), lg2_fast(hi2(v))); }
+__device__ __forceinline__ f32x2 ex2_2(f32x2 v) { return pk2(ex2_fast(lo2(v)), ex2_fast(hi2(v))); }
+
+// Midpoint expansion of the digamma function: psi(x + 1/2) = ln x + 1/(24 x^2) - 7/(960 x^4) + O(x^-6)
+// (next term 31/(8064 x^6) < 1.4e-7 for x >= 5.5).  It has no odd powers, so a count costs three packed
+// operations: acc += psi(x + 1/2) - ln x with w = 1/x.
+__device__ __forceinline__ f32x2 psi_mid_acc2(f32x2 w, f32x2 acc) {
+    const f32x2 u = mul2(w, w);
+    return fma2(u, fma2(u, dup2(-7.0f / 960.0f), dup2(1.0f / 24.0f)), acc);
+}
+
+// exp on pairs: one MUFU per value; 2^n is applied through the exponent field, so the argument is clamped to the
+// range in which the result stays a normal number (concentrations beyond e^-86 .. e^88 are rejected states anyway:
+// the value pass returns NaN above 1e6)
+__device__ __forceinline__ f32x2 exp2_acc(f32x2 x) {
+    const float xl = fminf(fmaxf(lo2(x), -86.0f), 88.0f), xh = fminf(fmaxf(hi2(x), -86.0f), 88.0f);
+    x = pk2(xl, xh);
+    const f32x2 tm = fma2(x, dup2(SCCODA_LOG2EF), dup2(12582912.0f));       // + 1.5 * 2^23: round to nearest integer
+    const f32x2 n = add2(tm, dup2(-12582912.0f));
+    f32x2 r = fma2(x, dup2(SCCODA_LOG2EF), mul2(n, dup2(-1.0f)));
+    r = fma2(x, dup2(1.925963033500011e-8f), r);                             // low part of log2(e)
+    const f32x2 p = ex2_2(r);
+    const int nl = __float_as_int(lo2(tm)) - 0x4B400000, nh = __float_as_int(hi2(tm)) - 0x4B400000;
+    return pk2(__int_as_float(__float_as_int(lo2(p)) + (nl << 23)), __int_as_float(__float_as_int(hi2(p)) + (nh << 23)));
+}
 
 // Two sums over the warp at once: lanes 0..15 return sum(a), lanes 16..31 return sum(b) (6 shuffles instead of 10).
 __device__ __forceinline__ float warp_sum2(float a, float b, int lane) {
@@ -28,6 +96,98 @@ __device__ __forceinline__ float warp_sum1(float v) {
     return v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Staging: the packed dataset (include/sccoda_b200.h) re-laid lane-major into shared memory (CcPlan, kernels.h)
+// ------------------------------------------------------------------------------------------------
+struct CcTile {
+    uint32_t cf, yv, ov, rows, el;   // shared-memory byte offsets (CcPlan)
+    int NT, NOT;                     // items / odd counts of the fullest pair of THIS dataset (loop bounds)
+    int N, NK, nbig;
+    float cnt0, cnt1;                // rows of the two covariate groups
+    double lconst;
+};
+
+// (group u, column) of pair index p = u*K + k (cell types) or 2K + u (row totals -> column K)
+__device__ __forceinline__ void cc_pair_to_col(int p, int K, int& u, int& col) {
+    if (p >= 2 * K) {
+        u = p - 2 * K;
+        col = K;
+    } else {
+        u = p >= K ? 1 : 0;
+        col = p - u * K;
+    }
+}
+
+__device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl, CcTile& t) {
+    using T = float;
+    const int N = a.dm.N, K = a.dm.K, NK = a.dm.NK, NP = 2 * (K + 1);
+    t.cf = (uint32_t)pl.cf; t.yv = (uint32_t)pl.yv; t.ov = (uint32_t)pl.ov; t.rows = (uint32_t)pl.rows; t.el = (uint32_t)pl.el;
+    t.N = N; t.NK = NK;
+    int* bounds = sp<int>((uint32_t)pl.bounds);   // [0]: items, [1]: odd counts of the fullest pair of this dataset
+    if (threadIdx.x < 2) bounds[threadIdx.x] = 0;
+    t.nbig = a.nbig[b];
+    t.lconst = a.lconst[b];
+    const int* rstart = a.rstart + (size_t)b * 3;
+    t.cnt0 = (float)(rstart[1] - rstart[0]);
+    t.cnt1 = (float)(rstart[2] - rstart[1]);
+    float* cf = sp<float>(t.cf);
+    float* yv = sp<float>(t.yv);
+    float* ov = sp<float>((uint32_t)pl.ov);
+    const T* pcoef = static_cast<const T*>(a.pcoef) + (size_t)b * NP * 6;
+    // rational coefficients: cf[j][lane] = (pair (0,lane), pair (1,lane)); lane K = row totals; lanes > K: zero
+    for (int i = threadIdx.x; i < 6 * 32 * 2; i += blockDim.x) {
+        const int u = i & 1, lane = (i >> 1) & 31, j = i >> 6;
+        float v = 0.0f;
+        if (lane <= K) v = pcoef[(lane < K ? u * K + lane : 2 * K + u) * 6 + j];
+        cf[i] = v;
+    }
+    // item and odd counts: padding is the count 6, which contributes psi(c+6) - psi(c+6) = 0
+    for (int i = threadIdx.x; i < a.NT * kItemR * 64; i += blockDim.x) yv[i] = 6.0f;
+    for (int i = threadIdx.x; i < a.NOT * 64; i += blockDim.x) ov[i] = 6.0f;
+    __syncthreads();
+    const T* iy = static_cast<const T*>(a.iy) + (size_t)b * kItemR * a.NImax;
+    const uint16_t* ipair = a.ipair + (size_t)b * a.NImax;
+    const uint16_t* ipos = a.ipos + (size_t)b * a.NImax;
+    const int NI = a.NI[b];
+    for (int i = threadIdx.x; i < NI * kItemR; i += blockDim.x) {
+        const int j = i / NI, it = i - j * NI;
+        const int p = ipair[it], tt = ipos[it] - p * a.NF;
+        int u, col;
+        cc_pair_to_col(p, K, u, col);
+        yv[((tt * kItemR + j) * 32 + col) * 2 + u] = iy[j * a.NImax + it];
+        if (j == 0) atomicMax(&bounds[0], tt + 1);
+    }
+    const int NG = a.NG[b];
+    const T* oy = static_cast<const T*>(a.oy) + (size_t)b * a.NOmax;
+    for (int q = threadIdx.x; q < NG; q += blockDim.x) {
+        const uint32_t od = a.odesc[(size_t)b * a.NGmax + q];
+        int u, col;
+        cc_pair_to_col(a.opair[(size_t)b * a.NGmax + q], K, u, col);
+        for (int tt = 0; tt < (int)(od >> 16); ++tt) ov[(tt * 32 + col) * 2 + u] = oy[(od & 0xffffu) + tt];
+        atomicMax(&bounds[1], (int)(od >> 16));
+    }
+    // value pass: rows (total, group) and elements (count, host constant, concentration slot u*32 + k)
+    float2* rows = sp<float2>(t.rows);
+    const T* ntot = static_cast<const T*>(a.ntot) + (size_t)b * N;
+    const int* grp = a.grp + (size_t)b * N;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) rows[n] = make_float2(ntot[n], __int_as_float(grp[n]));
+    float4* el = sp<float4>(t.el);
+    const T* ey = static_cast<const T*>(a.ey) + (size_t)b * NK;
+    const T* eycst = static_cast<const T*>(a.eycst) + (size_t)b * NK;
+    const uint32_t* eidx = a.eidx + (size_t)b * NK;
+    for (int e = threadIdx.x; e < NK; e += blockDim.x) {
+        const int uk = (int)(eidx[e] & 0xffffu);
+        const int u = uk >= K ? 1 : 0;
+        el[e] = make_float4(ey[e], eycst[e], __int_as_float(u * 32 + (uk - u * K)), 0.0f);
+    }
+    __syncthreads();
+    t.NT = bounds[0];
+    t.NOT = bounds[1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient
+// ------------------------------------------------------------------------------------------------
 // The four parameters a lane owns: alpha_k, b_offset_k, ind_raw_k (zero on the reference lane and on lanes >= K)
 // and sigma_d (uniform).
 struct CcVec {
@@ -35,104 +195,201 @@ struct CcVec {
 };
 
 struct CcLane {
-    int k, j;            // cell type, its index among the non-reference cell types
-    bool has, active;    // k < K; k < K and k != ref
+    int K;
+    bool has, active;    // lane < K; lane < K and lane != ref
     float x0, x1;        // the covariate value of the two groups
 };
 
-// Gradient of the log-density at q, pair / item layout (grouped.cuh).  Leaves the pair records
-// (concentrations included) in shared memory for dm_value.
-__device__ __forceinline__ CcVec cc_grad(const Dims& dm, const DataTile<float>& dt, const ChainScratch& cs,
-                                         const CcLane& ln, const CcVec& q, int lane) {
-    constexpr int R = SCCODA_ITEM_R;
-    const int K = dm.K, tot0 = dt.tot0;
-    PairRec<float>* prec = sp<PairRec<float>>(cs.cp);
-    float* A = sp<float>(cs.G);
-    const float* pcoef = sp<float>(dt.pcoef);
-    const float* iy = sp<float>(dt.iy);
-    const uint16_t* ipair = sp<uint16_t>(dt.ipair);
-    const uint16_t* ipos = sp<uint16_t>(dt.ipos);
+// sum_i W_i/(c+i) with ONE reciprocal: the three quadratics c(c+5), (c+1)(c+4), (c+2)(c+3) over their product
+// (overflows for c > ~2e6, where states are rejected anyway); cf = the lane's six packed coefficients
+__device__ __forceinline__ f32x2 pair_rational2(f32x2 c, const f32x2* __restrict__ cf) {
+    const f32x2 a = mul2(c, add2(c, dup2(5.0f)));
+    const f32x2 a4 = add2(a, dup2(4.0f)), a6 = add2(a, dup2(6.0f));
+    const f32x2 a46 = mul2(a4, a6);
+    const f32x2 n0 = fma2(cf[0 * 32], c, cf[1 * 32]), n1 = fma2(cf[2 * 32], c, cf[3 * 32]), n2 = fma2(cf[4 * 32], c, cf[5 * 32]);
+    const f32x2 t = fma2(n1, a6, mul2(n2, a4));
+    const f32x2 num = fma2(a, t, mul2(n0, a46));
+    return mul2(num, rcp2(mul2(a, a46)));
+}
 
+// Two items at once: sum_j [psi(c + y_j) - psi(c + 6)] for the R = 5 counts of each (all >= 6), with the midpoint
+// expansion at x_j = c + y_j - 1/2 (cm = c - 1/2); a = w^5 and nb = -5 (psi(x+1/2) - ln x) at x = c + 5.5, w = 1/x
+// refer the log-product and the series to c + 6 (cf. PairRec / item_eval in grouped.cuh).
+// Reciprocals: one MUFU for the first four counts (1/x_j = product of the others / product of all), one for the
+// fifth; one lg2 of the product ratio.
+__device__ __forceinline__ f32x2 item_eval2(f32x2 cm, f32x2 a, f32x2 nb, const f32x2* __restrict__ y) {
+    static_assert(SCCODA_ITEM_R == 5, "item_eval2 is written for 5 counts per item");
+    f32x2 z[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) z[j] = add2(cm, y[j * 32]);
+    const f32x2 p01 = mul2(z[0], z[1]), p23 = mul2(z[2], z[3]);
+    const f32x2 r = rcp2(mul2(p01, p23));
+    const f32x2 r01 = mul2(p23, r), r23 = mul2(p01, r);
+    f32x2 acc = nb;
+    acc = psi_mid_acc2(mul2(z[1], r01), acc);
+    acc = psi_mid_acc2(mul2(z[0], r01), acc);
+    acc = psi_mid_acc2(mul2(z[3], r23), acc);
+    acc = psi_mid_acc2(mul2(z[2], r23), acc);
+    acc = psi_mid_acc2(rcp2(z[4]), acc);
+    const f32x2 prod = mul2(mul2(p01, a), mul2(p23, z[4]));
+    return fma2(lg2_2(prod), dup2(SCCODA_LN2F), acc);
+}
+
+struct CcGrad {
+    CcVec g;
+    f32x2 c;   // concentrations of the lane's two pairs (lane K: S_0, S_1)
+};
+
+// Gradient of the log-density at q in the pair / item formulation of grouped.cuh.
+__device__ __forceinline__ CcGrad cc_grad(const CcTile& t, const CcLane& ln, const CcVec& q, int lane) {
     // spike-and-slab effect of the lane's cell type                                             (:724-734)
     const float id = ln.active ? sigmoid_stable(50.0f * q.i) : 0.0f;
     const float bet = id * q.s * q.b;
-    // concentrations and pair records of the two groups                                        (:743)
-    const int kc = ln.has ? ln.k : 0;
-    const float c0 = exp_acc(fmaf(ln.x0, bet, q.a)), c1 = exp_acc(fmaf(ln.x1, bet, q.a));
-    const PairRec<float> r0 = make_rec(c0, pcoef + 6 * kc), r1 = make_rec(c1, pcoef + 6 * (K + kc));
-    if (ln.has) {
-        prec[kc] = r0;
-        prec[K + kc] = r1;
-    }
-    // total pairs: S_u = sum_k c_uk; lanes 0..15 hold S_0, lanes 16..31 hold S_1
-    const float S = warp_sum2(ln.has ? c0 : 0.0f, ln.has ? c1 : 0.0f, lane);
-    if ((lane & 15) == 0) {
-        const int pt = tot0 + (lane >> 4);
-        prec[pt] = make_rec(S, pcoef + 6 * pt);
-    }
-    __syncwarp();
-    // items and odd groups, each into its own result slot
-    {
-        const int NIs = dt.NImax;
+    // concentrations of the two groups (:743); lane K takes the row sums S_u = sum_k c_uk
+    f32x2 c = exp2_acc(fma2(pk2(ln.x0, ln.x1), dup2(bet), dup2(q.a)));
+    const float c0 = ln.has ? lo2(c) : 0.0f, c1 = ln.has ? hi2(c) : 0.0f;
+    const float S = warp_sum2(c0, c1, lane);                                  // lanes 0..15: S_0, lanes 16..31: S_1
+    const float So = __shfl_xor_sync(0xffffffffu, S, 16);
+    if (lane == ln.K) c = lane < 16 ? pk2(S, So) : pk2(So, S);
+    // reference point of the items: x6 = c + 5.5, w6 = 1/x6, a = w6^5, nb = -5 (psi(c+6) - ln x6)
+    const f32x2* cf = sp<f32x2>(t.cf) + lane;
+    const f32x2 cm = add2(c, dup2(-0.5f));
+    const f32x2 w6 = rcp2(add2(c, dup2(5.5f)));
+    const f32x2 w62 = mul2(w6, w6);
+    const f32x2 a5 = mul2(mul2(w62, w62), w6);
+    const f32x2 nb = mul2(psi_mid_acc2(w6, dup2(0.0f)), dup2(-(float)SCCODA_ITEM_R));
+    // brackets Br = rational sum_i W_i/(c+i) + items + odd counts, both groups at once
+    f32x2 br = pair_rational2(c, cf);
+    const f32x2* yv = sp<f32x2>(t.yv) + lane;
 #pragma unroll 1
-        for (int i = lane; i < dt.NI; i += 32) {
-            const PairRec<float> r = prec[ipair[i]];
-            float y[R];
-#pragma unroll
-            for (int jj = 0; jj < R; ++jj) y[jj] = iy[jj * NIs + i];
-            A[ipos[i]] = item_eval(r, y);
-        }
+    for (int tt = 0; tt < t.NT; ++tt, yv += SCCODA_ITEM_R * 32) br = add2(br, item_eval2(cm, a5, nb, yv));
+    yv = sp<f32x2>(t.ov) + lane;
+    if (t.NOT > 0) {
+        // counts below 6 that are not in {0..5} (the 0.5 pseudocount, non-integer data): psi(c+y) - psi(c+6) one by one
+        const float d0 = digamma_big(lo2(c) + 6.0f), d1 = digamma_big(hi2(c) + 6.0f);
 #pragma unroll 1
-        for (int qd = lane; qd < dt.NG; qd += 32) {
-            const PairRec<float> r = prec[dt.opair[qd]];
-            const uint32_t od = dt.odesc[qd];
-            const float* oy = dt.oy + (od & 0xffffu);
-            float s = 0.0f;
-#pragma unroll 1
-            for (int t = 0; t < (int)(od >> 16); ++t) s += odd_eval(r, oy[t]);
-            A[dt.opos[qd]] = s;
+        for (int tt = 0; tt < t.NOT; ++tt, yv += 32) {
+            const f32x2 y = *yv;
+            br = add2(br, pk2(digamma_pos(lo2(c) + lo2(y)) - d0, digamma_pos(hi2(c) + hi2(y)) - d1));
         }
     }
-    __syncwarp();
     // d logp / d log c_uk = c_uk (Br_uk - Br_total(u)), chain rule
-    const int NF = dt.NF;   // 2 or 4 result slots per pair
-    const float bt0 = pair_bracket<float>(prec[tot0].rat, A + NF * tot0, NF);
-    const float bt1 = pair_bracket<float>(prec[tot0 + 1].rat, A + NF * (tot0 + 1), NF);
-    const float b0 = pair_bracket<float>(r0.rat, A + NF * kc, NF);
-    const float b1 = pair_bracket<float>(r1.rat, A + NF * (K + kc), NF);
-    const float G0 = ln.has ? c0 * (b0 - bt0) : 0.0f, G1 = ln.has ? c1 * (b1 - bt1) : 0.0f;
-    CcVec g;
-    g.a = fmaf(q.a, -0.04f, G0 + G1);                                      // d/d alpha_k   (0 on lanes >= K)
-    const float t = fmaf(ln.x0, G0, ln.x1 * G1) * id;                      // id == 0 on inactive lanes
-    g.b = fmaf(t, q.s, -q.b);                                              // d/d b_offset_k
-    g.i = fmaf(t * q.s * q.b, 50.0f * (1.0f - id), -q.i);                  // d/d ind_raw_k
+    const float bt0 = __shfl_sync(0xffffffffu, lo2(br), ln.K), bt1 = __shfl_sync(0xffffffffu, hi2(br), ln.K);
+    const float G0 = c0 * (lo2(br) - bt0), G1 = c1 * (hi2(br) - bt1);        // c0 = c1 = 0 on lanes >= K
+    CcGrad out;
+    out.c = c;
+    out.g.a = fmaf(q.a, -0.04f, G0 + G1);                                      // d/d alpha_k
+    const float tg = fmaf(ln.x0, G0, ln.x1 * G1) * id;                         // id == 0 on inactive lanes
+    out.g.b = fmaf(tg, q.s, -q.b);                                             // d/d b_offset_k
+    out.g.i = fmaf(tg * q.s * q.b, 50.0f * (1.0f - id), -q.i);                 // d/d ind_raw_k
     // d/d sigma_d: sum_k g_k ind_k b_offset_k - HalfCauchy term (zero prior gradient below 0 [TFP])
-    g.s = warp_sum1(t * q.b) - (q.s >= 0.0f ? 2.0f * q.s / (1.0f + q.s * q.s) : 0.0f);
-    return g;
+    out.g.s = warp_sum1(tg * q.b) - (q.s >= 0.0f ? 2.0f * q.s / (1.0f + q.s * q.s) : 0.0f);
+    return out;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Value of the log-density (same terms, guards and precision strategy as dm_value in model.cuh)
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool has, float qa, float qb, float qi, float qs,
+                                        f32x2 c, int K, int lane) {
+    float* pc = sp<float>(pc_off);
+    const float c0 = lo2(c), c1 = hi2(c);
+    __syncwarp();
+    pc[lane] = c0;            // slot u*32 + column; column K holds S_u
+    pc[32 + lane] = c1;
+    __syncwarp();
+    double lp = 0.0;
+    // priors (:703-741); the theta-independent constants live in lconst.  Parameters a lane does not own are zero.
+    lp += (double)fmaf(qa * qa, -0.02f, -0.5f * fmaf(qb, qb, qi * qi));
+    if (lane == 0 && qs >= 0.0f) lp -= log1p((double)qs * (double)qs);
+    // DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c)                               (:746-751)
+    // Guard (numerics): beyond c_max the lgamma differences have lost all precision => NaN => rejected.
+    const float c_max = 1e6f, c_joint = SCCODA_C_JOINT;
+    bool need_fix = false, bad = false;
+    if (has) {
+        float acc = 0.0f;
+        if (c0 < c_joint) acc = -t.cnt0 * lgamma_pos(c0); else need_fix = true;
+        if (c1 < c_joint) acc = fmaf(-t.cnt1, lgamma_pos(c1), acc); else need_fix = true;
+        bad = !(c0 <= c_max) || !(c1 <= c_max);
+        lp += (double)acc;
+    }
+    if (bad) lp = CUDART_NAN;
+    {
+        const float S0 = pc[K], S1 = pc[32 + K];
+        const float2* rows = sp<float2>(t.rows);
+#pragma unroll 1
+        for (int n = lane; n < t.N; n += 32) {
+            const float2 r = rows[n];
+            lp += lgamma_rowdiff_f64((double)(__float_as_int(r.y) ? S1 : S0), (double)r.x);
+        }
+    }
+    {
+        const float4* el = sp<float4>(t.el);
+        float acc = 0.0f;
+#pragma unroll 2
+        for (int e = lane; e < t.nbig; e += 32) {
+            const float4 v = el[e];
+            acc += lgamma_shift_big(pc[__float_as_int(v.z)], v.x, v.y);
+        }
+#pragma unroll 1
+        for (int e = t.nbig + lane; e < t.NK; e += 32) {
+            const float4 v = el[e];
+            acc += lgamma_shift(pc[__float_as_int(v.z)], v.x, v.y);
+        }
+        lp += (double)acc;
+        if (__any_sync(0xffffffffu, need_fix)) {
+            // concentrations >= c_joint (rare): joint cancellation-free form, which also carries the -lgamma(c)
+            double fix = 0.0;
+#pragma unroll 1
+            for (int e = lane; e < t.NK; e += 32) {
+                const float4 v = el[e];
+                const float cc = pc[__float_as_int(v.z)];
+                if (cc >= c_joint) fix += (double)lgamma_joint(cc, v.x, v.y) - (double)lgamma_shift(cc, v.x, v.y);
+            }
+            lp += fix;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    lp += t.lconst;
+    if (qs < 0.0f) lp = -CUDART_INF;   // HalfCauchy support [TFP]
+    return lp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ KArgs a) {
     using T = float;
-    DataTile<T> dt;
-    ChainScratch cs;
-    Group<1> g;
-    int b, c;
-    if (!prologue<T, 1>(a, 1, dt, cs, g, b, c)) return;
-    const int lane = g.tid;
+    const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
+    const int cpc = blockDim.x >> 5;
+    const int ctas_per_ds = (a.C + cpc - 1) / cpc;
+    const int b = blockIdx.x / ctas_per_ds;
+    const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
     const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P;
-    T* const vec = sp<T>(cs.vec);                 // one flat state vector: momentum transpose, theta for dm_value
+    const CcPlan pl = plan_cc(a.dm.N, K, a.NT, a.NOT);
+    CcTile tile;
+    cc_stage(a, b, pl, tile);
+    if (c >= a.C) return;
+    const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
+    const uint32_t pc_off = chain_off + (uint32_t)pl.pc;
+    T* const vec = sp<T>(chain_off + (uint32_t)pl.vec);   // one flat state vector: momentum transpose, carry in / out
     const size_t chain = (size_t)b * a.C + c;
     const RngKey key{(uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), a.chain_id0 + (uint32_t)chain};
+    const int ref = a.ref[b];
 
     CcLane ln;
-    ln.k = lane;
+    ln.K = K;
     ln.has = lane < K;
-    ln.active = ln.has && lane != dt.ref;
-    ln.j = lane - (lane > dt.ref);
-    ln.x0 = sp<T>(dt.xu)[0];
-    ln.x1 = dt.U > 1 ? sp<T>(dt.xu)[1] : T(0);
+    ln.active = ln.has && lane != ref;
+    {
+        const T* xu = static_cast<const T*>(a.xu) + (size_t)b * 2;
+        ln.x0 = xu[0];
+        ln.x1 = a.U[b] > 1 ? xu[1] : T(0);
+    }
     // flat indices of the lane's parameters (order of scCODA_model.py:692-693 with D == 1)
-    const int ix_b = 1 + ln.j, ix_i = 1 + K1 + ln.j, ix_a = 1 + 2 * K1 + ln.k;
+    const int jj = lane - (lane > ref);
+    const int ix_b = 1 + jj, ix_i = 1 + K1 + jj, ix_a = 1 + 2 * K1 + lane;
 
     auto gather = [&](const T* v) {               // flat shared-memory vector -> lane registers
         CcVec r;
@@ -187,31 +444,30 @@ __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ 
             q.a = fmaf(eps, m.a, thc.a); q.b = fmaf(eps, m.b, thc.b); q.i = fmaf(eps, m.i, thc.i); q.s = fmaf(eps, m.s, thc.s);
         }
         const int nl = boot ? 1 : L;
-        CcVec gq;
+        CcGrad gr;
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
-            gq = cc_grad(a.dm, dt, cs, ln, q, lane);
+            gr = cc_grad(tile, ln, q, lane);
             if (!boot) {
                 const bool last = (l == nl - 1);
                 const T f = last ? T(0.5) * eps : eps;
-                m.a = fmaf(f, gq.a, m.a); m.b = fmaf(f, gq.b, m.b); m.i = fmaf(f, gq.i, m.i); m.s = fmaf(f, gq.s, m.s);
+                m.a = fmaf(f, gr.g.a, m.a); m.b = fmaf(f, gr.g.b, m.b); m.i = fmaf(f, gr.g.i, m.i); m.s = fmaf(f, gr.g.s, m.s);
                 if (!last) {
                     q.a = fmaf(eps, m.a, q.a); q.b = fmaf(eps, m.b, q.b); q.i = fmaf(eps, m.i, q.i); q.s = fmaf(eps, m.s, q.s);
                 }
             }
         }
-        // value at the end point (dm_value reads theta from shared memory and the concentrations cc_grad left)
-        __syncwarp();
-        scatter(vec, q);
-        __syncwarp();
-        const double lp_new = dm_value<T, 1, PairRec<T>>(a.dm, dt, cs, cs.vec, g);
+        // value at the end point, from the concentrations of the last gradient evaluation
+        const double lp_new = cc_value(tile, pc_off, ln.has, q.a, q.b, q.i, q.s, gr.c, K, lane);
         bool acc = true;
         double lar = 0.0;
         if (!boot) {
             // kinetic energies: the momenta of sigma_d are replicated, count them once
             kin -= fmaf(m.a, m.a, fmaf(m.b, m.b, m.i * m.i));
             if (lane == 0) kin -= m.s * m.s;
-            const double dkin = g.sum((double)kin);
+            double dkin = (double)kin;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dkin += __shfl_xor_sync(0xffffffffu, dkin, o);
             // [TFP] log_accept_ratio = safe_sum([logp', -logp, kinetic - kinetic']); non-finite -> -inf
             lar = lp_new - lp_cur + 0.5 * dkin;
             if (!isfinite(lar)) lar = -CUDART_INF;
@@ -220,7 +476,7 @@ __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ 
         }
         if (acc) {
             thc = q;
-            gc = gq;
+            gc = gr.g;
             lp_cur = lp_new;
         }
         if (boot) continue;

@@ -13,14 +13,18 @@ int nvec_for(int kind, int max_depth) {
 }
 
 int select_kind(const KArgs& a, int kind, int dtype, int W) {
-    if (kind == KIND_HMC && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 && a.dm.D == 1 && a.Umax <= 2 &&
-        a.dm.K <= 32 && a.NF <= 4)
+    if (kind == KIND_HMC && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 && a.dm.D == 1 && a.Umax == 2 &&
+        a.dm.K <= 31)
         return KIND_HMC_CC;
     return kind;
 }
 
 size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int dtype) {
     const size_t ts = dtype == SCCODA_F64 ? 8 : 4;
+    if (kind == KIND_HMC_CC) {
+        const CcPlan cp = plan_cc(a.dm.N, a.dm.K, a.NT, a.NOT);
+        return cp.data_total + (size_t)chains_per_cta * cp.chain_total;
+    }
     const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem, a.grouped ? a.NImax : 0, a.NF,
                                   nvec_for(kind, a.max_depth), W, ts);
     return pl.data_total + (size_t)chains_per_cta * pl.chain_total;

@@ -20,7 +20,7 @@ struct KArgs {
     int B, C, Umax;
     int el_smem;  // 1: stage the element list into shared memory (fp32 build, when it fits); 0: read it from global
     int grouped;  // 1: pair / item gradient path (grouped.cuh); 0: element path (model.cuh)
-    int NImax, NOmax, NGmax, NF;
+    int NImax, NOmax, NGmax, NF, NT, NOT;
     const int* NI;
     const void* iy;
     const uint16_t* ipair;
@@ -99,6 +99,27 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
     p.gk = o; o += grouped ? 0 : rnd16((size_t)(D + 1) * K * ts);
     p.vec = o; o += rnd16((size_t)nvec * rnd16(P * ts));
     p.chain_total = o;
+    return p;
+}
+
+// Shared-memory plan of the case/control HMC kernel (hmc_cc.cuh): lane-major arrays at compile-time offsets first.
+struct CcPlan {
+    size_t cf, yv, ov, rows, el, bounds, data_total;   // per CTA
+    size_t pc, vec, chain_total;               // per chain (relative)
+};
+__host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT) {
+    CcPlan p;
+    size_t o = 0;
+    p.cf = o; o += 6 * 32 * 8;                                   // f32x2[6][32] rational coefficients (group 0, group 1)
+    p.yv = o; o += (size_t)NT * kItemR * 32 * 8;                 // f32x2[NT][R][32] item counts
+    p.ov = o; o += (size_t)NOT * 32 * 8;                         // f32x2[NOT][32] odd counts (directly after the items)
+    p.rows = o; o += rnd16((size_t)N * 8);                       // (row total, group)
+    p.el = o; o += (size_t)N * K * 16;                           // (count, host constant, concentration slot, -)
+    p.bounds = o; o += 16;                                       // int[2]: per-dataset loop bounds (items, odd counts)
+    p.data_total = o;
+    p.pc = 0;                                                    // float[64] concentrations, slot u*32 + column
+    p.vec = 256;                                                 // float[96] flat state vector
+    p.chain_total = 256 + 384;
     return p;
 }
 

@@ -13,11 +13,12 @@ import sys
 
 # (file, first line, last line, label) — edit when the sources move
 PHASES = [
-    ("hmc_cc.cuh", 56, 59, "cc: effects"),
-    ("hmc_cc.cuh", 60, 73, "cc: pair records + totals"),
-    ("hmc_cc.cuh", 74, 96, "cc: items"),
-    ("hmc_cc.cuh", 97, 112, "cc: brackets + chain rule"),
-    ("hmc_cc.cuh", 113, 400, "cc: sampler (momentum, leapfrog, accept, adapt, trace)"),
+    ("hmc_cc.cuh", 236, 239, "cc: effects"),
+    ("hmc_cc.cuh", 240, 251, "cc: concentrations, totals, pair records"),
+    ("hmc_cc.cuh", 252, 266, "cc: rational + items + odd counts"),
+    ("hmc_cc.cuh", 267, 283, "cc: chain rule"),
+    ("hmc_cc.cuh", 284, 352, "cc: value"),
+    ("hmc_cc.cuh", 353, 600, "cc: sampler (momentum, leapfrog, accept, adapt, trace)"),
     ("grouped.cuh", 130, 169, "P0 effects (grouped)"),
     ("grouped.cuh", 170, 216, "P1 pair records + totals (grouped)"),
     ("grouped.cuh", 217, 239, "E items (grouped)"),
