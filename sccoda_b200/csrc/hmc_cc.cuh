@@ -66,6 +66,19 @@ __device__ __forceinline__ f32x2 psi_mid_acc2(f32x2 w, f32x2 acc) {
     return fma2(u, fma2(u, dup2(-7.0f / 960.0f), dup2(1.0f / 24.0f)), acc);
 }
 
+// psi(x) on pairs for any x > 0: below 6 the recurrence psi(x) = psi(x+6) - sum_{i<6} 1/(x+i) with the sum as ONE
+// rational (digamma_pos in special.cuh), then the midpoint expansion at x (+6) - 1/2
+__device__ __forceinline__ f32x2 psi_any2(f32x2 x) {
+    const f32x2 a = mul2(x, add2(x, dup2(5.0f)));
+    const f32x2 P = mul2(mul2(a, add2(a, dup2(4.0f))), add2(a, dup2(6.0f)));
+    const f32x2 Nn = mul2(fma2(fma2(dup2(3.0f), a, dup2(20.0f)), a, dup2(24.0f)), fma2(dup2(2.0f), x, dup2(5.0f)));
+    const f32x2 corr = mul2(Nn, rcp2(P));
+    const bool sl = lo2(x) < 6.0f, sh = hi2(x) < 6.0f;
+    const f32x2 xm = add2(x, pk2(sl ? 5.5f : -0.5f, sh ? 5.5f : -0.5f));
+    const f32x2 v = fma2(lg2_2(xm), dup2(SCCODA_LN2F), psi_mid_acc2(rcp2(xm), dup2(0.0f)));
+    return add2(v, pk2(sl ? -lo2(corr) : 0.0f, sh ? -hi2(corr) : 0.0f));
+}
+
 // exp on pairs: one MUFU per value; 2^n is applied through the exponent field, so the argument is clamped to the
 // range in which the result stays a normal number (concentrations beyond e^-86 .. e^88 are rejected states anyway:
 // the value pass returns NaN above 1e6)
@@ -123,10 +136,9 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
     const int N = a.dm.N, K = a.dm.K, NK = a.dm.NK, NP = 2 * (K + 1);
     t.cf = (uint32_t)pl.cf; t.yv = (uint32_t)pl.yv; t.ov = (uint32_t)pl.ov; t.rows = (uint32_t)pl.rows; t.el = (uint32_t)pl.el;
     t.N = N; t.NK = NK;
-    int* bounds = sp<int>((uint32_t)pl.bounds);   // [0]: items, [1]: odd counts of the fullest pair of this dataset
+    // [0]: items, [1]: odd counts of the fullest pair of this dataset, [2]: elements with a count >= 6
+    int* bounds = sp<int>((uint32_t)pl.bounds);
     if (threadIdx.x < 2) bounds[threadIdx.x] = 0;
-    t.nbig = a.nbig[b];
-    t.lconst = a.lconst[b];
     const int* rstart = a.rstart + (size_t)b * 3;
     t.cnt0 = (float)(rstart[1] - rstart[0]);
     t.cnt1 = (float)(rstart[2] - rstart[1]);
@@ -166,23 +178,58 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
         for (int tt = 0; tt < (int)(od >> 16); ++tt) ov[(tt * 32 + col) * 2 + u] = oy[(od & 0xffffu) + tt];
         atomicMax(&bounds[1], (int)(od >> 16));
     }
-    // value pass: rows (total, group) and elements (count, host constant, concentration slot u*32 + k)
-    float2* rows = sp<float2>(t.rows);
+    // value pass, rows: (total n, r(n) or lgamma(n) as in _pack.py's eycst, group); the row terms are evaluated as
+    // -[lgamma(S+n) - lgamma(S) - lgamma(n)] in fp32 (cancellation-free), so sum_n lgamma(n) moves into the constant
+    float4* rows = sp<float4>(t.rows);
     const T* ntot = static_cast<const T*>(a.ntot) + (size_t)b * N;
     const int* grp = a.grp + (size_t)b * N;
-    for (int n = threadIdx.x; n < N; n += blockDim.x) rows[n] = make_float2(ntot[n], __int_as_float(grp[n]));
+    double lg_sum = 0.0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const double nn = (double)ntot[n];
+        const double lg = lgamma(nn);
+        const double rc = nn >= 6.0 ? lg - ((nn - 0.5) * log(nn) - nn + 0.91893853320467274178) : lg;
+        rows[n] = make_float4((float)nn, (float)rc, __int_as_float(grp[n]), 0.0f);
+        lg_sum += lg;
+    }
+    double* red = sp<double>((uint32_t)pl.red);
+    if (threadIdx.x < 4) red[threadIdx.x] = 0.0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) lg_sum += __shfl_xor_sync(0xffffffffu, lg_sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lg_sum;   // one slot per warp: deterministic sum below
+    // value pass, elements: (count, host constant, concentration slot u*32 + k), counts >= 6 first.  The partition
+    // is done by warp 0 with ballots, in list order, so that the summation order never depends on the launch.
     float4* el = sp<float4>(t.el);
     const T* ey = static_cast<const T*>(a.ey) + (size_t)b * NK;
     const T* eycst = static_cast<const T*>(a.eycst) + (size_t)b * NK;
     const uint32_t* eidx = a.eidx + (size_t)b * NK;
-    for (int e = threadIdx.x; e < NK; e += blockDim.x) {
-        const int uk = (int)(eidx[e] & 0xffffu);
-        const int u = uk >= K ? 1 : 0;
-        el[e] = make_float4(ey[e], eycst[e], __int_as_float(u * 32 + (uk - u * K)), 0.0f);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int nbig = 0;
+        for (int base = 0; base < NK; base += 32) nbig += __popc(__ballot_sync(0xffffffffu, base + lane < NK && ey[base + lane] >= 6.0f));
+        int ib = 0, is = nbig;
+        for (int base = 0; base < NK; base += 32) {
+            const int e = base + lane;
+            const bool in = e < NK;
+            const float y = in ? ey[e] : 0.0f;
+            const bool big = in && y >= 6.0f;
+            const uint32_t mb = __ballot_sync(0xffffffffu, big), ms = __ballot_sync(0xffffffffu, in && !big);
+            const uint32_t lt = (1u << lane) - 1u;
+            if (in) {
+                const int uk = (int)(eidx[e] & 0xffffu);
+                const int u = uk >= K ? 1 : 0;
+                const int dst = big ? ib + __popc(mb & lt) : is + __popc(ms & lt);
+                el[dst] = make_float4(y, eycst[e], __int_as_float(u * 32 + (uk - u * K)), 0.0f);
+            }
+            ib += __popc(mb);
+            is += __popc(ms);
+        }
+        if (lane == 0) bounds[2] = nbig;
     }
     __syncthreads();
     t.NT = bounds[0];
     t.NOT = bounds[1];
+    t.nbig = bounds[2];
+    t.lconst = a.lconst[b] - (((red[0] + red[1]) + red[2]) + red[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -266,12 +313,10 @@ __device__ __forceinline__ CcGrad cc_grad(const CcTile& t, const CcLane& ln, con
     yv = sp<f32x2>(t.ov) + lane;
     if (t.NOT > 0) {
         // counts below 6 that are not in {0..5} (the 0.5 pseudocount, non-integer data): psi(c+y) - psi(c+6) one by one
-        const float d0 = digamma_big(lo2(c) + 6.0f), d1 = digamma_big(hi2(c) + 6.0f);
+        const f32x2 x6 = add2(c, dup2(5.5f));
+        const f32x2 nref = fma2(lg2_2(x6), dup2(-SCCODA_LN2F), mul2(nb, dup2(1.0f / (float)SCCODA_ITEM_R)));   // -psi(c+6)
 #pragma unroll 1
-        for (int tt = 0; tt < t.NOT; ++tt, yv += 32) {
-            const f32x2 y = *yv;
-            br = add2(br, pk2(digamma_pos(lo2(c) + lo2(y)) - d0, digamma_pos(hi2(c) + hi2(y)) - d1));
-        }
+        for (int tt = 0; tt < t.NOT; ++tt, yv += 32) br = add2(br, add2(psi_any2(add2(c, *yv)), nref));
     }
     // d logp / d log c_uk = c_uk (Br_uk - Br_total(u)), chain rule
     const float bt0 = __shfl_sync(0xffffffffu, lo2(br), ln.K), bt1 = __shfl_sync(0xffffffffu, hi2(br), ln.K);
@@ -283,7 +328,7 @@ __device__ __forceinline__ CcGrad cc_grad(const CcTile& t, const CcLane& ln, con
     out.g.b = fmaf(tg, q.s, -q.b);                                             // d/d b_offset_k
     out.g.i = fmaf(tg * q.s * q.b, 50.0f * (1.0f - id), -q.i);                 // d/d ind_raw_k
     // d/d sigma_d: sum_k g_k ind_k b_offset_k - HalfCauchy term (zero prior gradient below 0 [TFP])
-    out.g.s = warp_sum1(tg * q.b) - (q.s >= 0.0f ? 2.0f * q.s / (1.0f + q.s * q.s) : 0.0f);
+    out.g.s = warp_sum1(tg * q.b) - (q.s >= 0.0f ? 2.0f * q.s * rcp_fast(fmaf(q.s, q.s, 1.0f)) : 0.0f);
     return out;
 }
 
@@ -315,13 +360,17 @@ __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool h
     }
     if (bad) lp = CUDART_NAN;
     {
+        // rows: -[lgamma(S_u + n) - lgamma(S_u) - lgamma(n)], joint form for S_u >= 6 (the usual case)
         const float S0 = pc[K], S1 = pc[32 + K];
-        const float2* rows = sp<float2>(t.rows);
+        const float4* rows = sp<float4>(t.rows);
+        float acc = 0.0f;
 #pragma unroll 1
         for (int n = lane; n < t.N; n += 32) {
-            const float2 r = rows[n];
-            lp += lgamma_rowdiff_f64((double)(__float_as_int(r.y) ? S1 : S0), (double)r.x);
+            const float4 r = rows[n];
+            const float S = __float_as_int(r.z) ? S1 : S0;
+            acc -= S >= 6.0f ? lgamma_joint(S, r.x, r.y) : lgamma_shift(S, r.x, r.y) - lgamma_pos(S);
         }
+        lp += (double)acc;
     }
     {
         const float4* el = sp<float4>(t.el);

@@ -104,7 +104,7 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
 
 // Shared-memory plan of the case/control HMC kernel (hmc_cc.cuh): lane-major arrays at compile-time offsets first.
 struct CcPlan {
-    size_t cf, yv, ov, rows, el, bounds, data_total;   // per CTA
+    size_t cf, yv, ov, rows, el, bounds, red, data_total;   // per CTA
     size_t pc, vec, chain_total;               // per chain (relative)
 };
 __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT) {
@@ -113,9 +113,10 @@ __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT) {
     p.cf = o; o += 6 * 32 * 8;                                   // f32x2[6][32] rational coefficients (group 0, group 1)
     p.yv = o; o += (size_t)NT * kItemR * 32 * 8;                 // f32x2[NT][R][32] item counts
     p.ov = o; o += (size_t)NOT * 32 * 8;                         // f32x2[NOT][32] odd counts (directly after the items)
-    p.rows = o; o += rnd16((size_t)N * 8);                       // (row total, group)
+    p.rows = o; o += (size_t)N * 16;                             // (row total, host-like constant, group, -)
     p.el = o; o += (size_t)N * K * 16;                           // (count, host constant, concentration slot, -)
-    p.bounds = o; o += 16;                                       // int[2]: per-dataset loop bounds (items, odd counts)
+    p.bounds = o; o += 16;                                       // int[3]: per-dataset loop bounds (items, odd counts, big elements)
+    p.red = o; o += 32;                                          // double[4]: staging reduction
     p.data_total = o;
     p.pc = 0;                                                    // float[64] concentrations, slot u*32 + column
     p.vec = 256;                                                 // float[96] flat state vector

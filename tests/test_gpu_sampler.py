@@ -162,6 +162,14 @@ def test_case_control_kernel_follows_generic_kernel(method):
                        outs[1].stat("target_log_prob").cpu().numpy()[:, :, :n], atol=5e-2)
     assert np.allclose(outs[0].stat("step_size").cpu().numpy()[:, :, :n],
                        outs[1].stat("step_size").cpu().numpy()[:, :, :n], rtol=1e-3)
+    # the traced log-density of the case/control kernel is the oracle's log-density at the traced state
+    from oracle import np_oracle as o
+    lp1 = outs[1].stat("target_log_prob").cpu().numpy()
+    for b in range(B):
+        m = o.prepare(xs[b], ys[b], int([19, 0, 7][b]))
+        for c in range(C):
+            ref = np.array([o.logp(d1[b, c, i].astype(np.float64), m) for i in range(16)])
+            assert np.abs(lp1[b, c] - ref).max() < 2e-3 * max(1.0, np.abs(ref).max() * 1e-3) + 4e-3, (b, c)
     # chunked resume of the case/control kernel is bit-identical to the single launch
     smp = prob.make_sampler(method, 16, 0, num_adapt=16, seed=3, warps_per_chain=1)
     many = prob.sample(init, smp, chunk=5)

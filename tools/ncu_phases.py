@@ -13,12 +13,12 @@ import sys
 
 # (file, first line, last line, label) — edit when the sources move
 PHASES = [
-    ("hmc_cc.cuh", 236, 239, "cc: effects"),
-    ("hmc_cc.cuh", 240, 251, "cc: concentrations, totals, pair records"),
-    ("hmc_cc.cuh", 252, 266, "cc: rational + items + odd counts"),
-    ("hmc_cc.cuh", 267, 283, "cc: chain rule"),
-    ("hmc_cc.cuh", 284, 352, "cc: value"),
-    ("hmc_cc.cuh", 353, 600, "cc: sampler (momentum, leapfrog, accept, adapt, trace)"),
+    ("hmc_cc.cuh", 244, 247, "cc: effects"),
+    ("hmc_cc.cuh", 248, 260, "cc: concentrations, totals, pair records"),
+    ("hmc_cc.cuh", 261, 275, "cc: rational + items + odd counts"),
+    ("hmc_cc.cuh", 276, 292, "cc: chain rule"),
+    ("hmc_cc.cuh", 293, 361, "cc: value"),
+    ("hmc_cc.cuh", 362, 600, "cc: sampler (momentum, leapfrog, accept, adapt, trace)"),
     ("grouped.cuh", 130, 169, "P0 effects (grouped)"),
     ("grouped.cuh", 170, 216, "P1 pair records + totals (grouped)"),
     ("grouped.cuh", 217, 239, "E items (grouped)"),
