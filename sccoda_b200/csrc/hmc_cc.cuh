@@ -79,6 +79,27 @@ __device__ __forceinline__ f32x2 psi_any2(f32x2 x) {
     return add2(v, pk2(sl ? -lo2(corr) : 0.0f, sh ? -hi2(corr) : 0.0f));
 }
 
+// lgamma(c + y) - lgamma(y) for two counts y >= 6 at once (lgamma_shift_big of special.cuh on pairs):
+//   (y - 1/2) log1p(c/y) + c (ln(c+y) - 1) + r(c+y) - r(y),   ycst = r(y) and yinv = 1/y from staging
+__device__ __forceinline__ f32x2 lgamma_shift_big2(f32x2 c, f32x2 y, f32x2 ycst, f32x2 yinv) {
+    const f32x2 z = add2(c, y);
+    const f32x2 w = rcp2(z);
+    const f32x2 t = mul2(c, yinv);
+    // log1p(t), t >= 0: ln(1+t) by MUFU for t >= 1/2, 2 atanh(t/(2+t)) as an odd series below (log1p_pos)
+    const f32x2 sq = mul2(t, rcp2(add2(t, dup2(2.0f))));
+    const f32x2 s2 = mul2(sq, sq);
+    f32x2 ser = fma2(s2, dup2(2.0f / 9.0f), dup2(2.0f / 7.0f));
+    ser = fma2(s2, ser, dup2(2.0f / 5.0f));
+    ser = fma2(s2, ser, dup2(2.0f / 3.0f));
+    ser = mul2(sq, fma2(s2, ser, dup2(2.0f)));
+    const f32x2 big = mul2(lg2_2(add2(t, dup2(1.0f))), dup2(SCCODA_LN2F));
+    const f32x2 l1p = pk2(lo2(t) >= 0.5f ? lo2(big) : lo2(ser), hi2(t) >= 0.5f ? hi2(big) : hi2(ser));
+    const f32x2 cterm = fma2(mul2(c, dup2(SCCODA_LN2F)), lg2_2(z), mul2(c, dup2(-1.0f)));     // c (ln z - 1)
+    const f32x2 w2 = mul2(w, w);
+    const f32x2 rem = mul2(w, fma2(w2, fma2(w2, dup2(1.0f / 1260.0f), dup2(-1.0f / 360.0f)), dup2(1.0f / 12.0f)));
+    return add2(fma2(add2(y, dup2(-0.5f)), l1p, cterm), add2(rem, mul2(ycst, dup2(-1.0f))));
+}
+
 // exp on pairs: one MUFU per value; 2^n is applied through the exponent field, so the argument is clamped to the
 // range in which the result stays a normal number (concentrations beyond e^-86 .. e^88 are rejected states anyway:
 // the value pass returns NaN above 1e6)
@@ -218,7 +239,7 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
                 const int uk = (int)(eidx[e] & 0xffffu);
                 const int u = uk >= K ? 1 : 0;
                 const int dst = big ? ib + __popc(mb & lt) : is + __popc(ms & lt);
-                el[dst] = make_float4(y, eycst[e], __int_as_float(u * 32 + (uk - u * K)), 0.0f);
+                el[dst] = make_float4(y, eycst[e], __int_as_float(u * 32 + (uk - u * K)), 1.0f / y);
             }
             ib += __popc(mb);
             is += __popc(ms);
@@ -346,7 +367,7 @@ __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool h
     double lp = 0.0;
     // priors (:703-741); the theta-independent constants live in lconst.  Parameters a lane does not own are zero.
     lp += (double)fmaf(qa * qa, -0.02f, -0.5f * fmaf(qb, qb, qi * qi));
-    if (lane == 0 && qs >= 0.0f) lp -= log1p((double)qs * (double)qs);
+    if (lane == 0 && qs >= 0.0f) lp -= (double)log1pf(qs * qs);
     // DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c)                               (:746-751)
     // Guard (numerics): beyond c_max the lgamma differences have lost all precision => NaN => rejected.
     const float c_max = 1e6f, c_joint = SCCODA_C_JOINT;
@@ -375,10 +396,21 @@ __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool h
     {
         const float4* el = sp<float4>(t.el);
         float acc = 0.0f;
-#pragma unroll 2
-        for (int e = lane; e < t.nbig; e += 32) {
-            const float4 v = el[e];
-            acc += lgamma_shift_big(pc[__float_as_int(v.z)], v.x, v.y);
+        {
+            // counts >= 6, two per lane and iteration on packed pairs; a last unpaired one alone
+            f32x2 acc2 = dup2(0.0f);
+            int e = lane;
+#pragma unroll 1
+            for (; e + 32 < t.nbig; e += 64) {
+                const float4 va = el[e], vb = el[e + 32];
+                acc2 = add2(acc2, lgamma_shift_big2(pk2(pc[__float_as_int(va.z)], pc[__float_as_int(vb.z)]), pk2(va.x, vb.x),
+                                                    pk2(va.y, vb.y), pk2(va.w, vb.w)));
+            }
+            acc = lo2(acc2) + hi2(acc2);
+            if (e < t.nbig) {
+                const float4 v = el[e];
+                acc += lgamma_shift_big(pc[__float_as_int(v.z)], v.x, v.y);
+            }
         }
 #pragma unroll 1
         for (int e = t.nbig + lane; e < t.NK; e += 32) {
@@ -520,8 +552,8 @@ __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ 
             // [TFP] log_accept_ratio = safe_sum([logp', -logp, kinetic - kinetic']); non-finite -> -inf
             lar = lp_new - lp_cur + 0.5 * dkin;
             if (!isfinite(lar)) lar = -CUDART_INF;
-            const double u = (double)rng_uniform<T>(key, 0u, (uint32_t)t, STREAM_ACCEPT);
-            acc = log(u) < lar;
+            const T u = rng_uniform<T>(key, 0u, (uint32_t)t, STREAM_ACCEPT);
+            acc = (double)logf((float)u) < lar;   // u is a 24-bit uniform, exact in fp32
         }
         if (acc) {
             thc = q;

@@ -19,10 +19,10 @@ PHASES = [
     ("hmc_cc.cuh", 276, 292, "cc: chain rule"),
     ("hmc_cc.cuh", 293, 361, "cc: value"),
     ("hmc_cc.cuh", 362, 600, "cc: sampler (momentum, leapfrog, accept, adapt, trace)"),
-    ("grouped.cuh", 130, 169, "P0 effects (grouped)"),
-    ("grouped.cuh", 170, 216, "P1 pair records + totals (grouped)"),
-    ("grouped.cuh", 217, 239, "E items (grouped)"),
-    ("grouped.cuh", 240, 320, "C columns + chain rule + epilogue (grouped)"),
+    ("grouped.cuh", 140, 177, "P0 effects (grouped)"),
+    ("grouped.cuh", 178, 224, "P1 pair records + totals (grouped)"),
+    ("grouped.cuh", 225, 247, "E items (grouped)"),
+    ("grouped.cuh", 248, 330, "C columns + chain rule + epilogue (grouped)"),
     ("model.cuh", 167, 203, "F1 effects"),
     ("model.cuh", 204, 266, "F2/F3 concentrations, row terms"),
     ("model.cuh", 267, 323, "E elements"),
