@@ -327,7 +327,7 @@ def run_ours(a):
                 "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None, "traffic": None,
                 "peak_source": "FFMA micro-kernel measured in this run on this device (sccoda_measure_peaks); "
                                "MEASURED_PEAKS.json has no fp32 entry",
-                "mufu_peak_tops": mufu_peak, "kernel": "hmc_kernel<float,W>", "kernel_ms": k_ms,
+                "mufu_peak_tops": mufu_peak, "kernel": {1: "hmc_kernel<float,W,grouped>", 3: "hmc_cc_kernel"}.get(out.kernel_kind, "hmc_kernel"), "kernel_ms": k_ms,
                 "algorithmic_flop_per_launch": flops_launch,
                 "flop_model": "per grad-eval 64NK+48N+4NKD, per value 28(2NK+2N) (SURVEY 8d)",
                 "hbm": {"achieved_gbs": draw_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),

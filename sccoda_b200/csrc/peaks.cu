@@ -24,9 +24,10 @@ __global__ void __launch_bounds__(256) mufu_peak_kernel(float* out, float a) {
     float x0 = threadIdx.x * 1e-3f + a, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
 #pragma unroll 16
     for (int i = 0; i < ITERS; ++i) {
+        // four independent chains; no rcp(rcp(x)) pairs, which ptxas folds away
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x0));
         asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(x1));
-        asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x2));
+        asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x2));
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x3));
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3;

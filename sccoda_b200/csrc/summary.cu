@@ -12,74 +12,131 @@
 
 namespace sccoda {
 
+// One CTA per chain.  Task t = one output group (a state coordinate, one beta_dk, one scalar statistic); the CTA's
+// threads are laid out as (row slice, task) so that short task lists (P + DK + 6 = 85 for K = 20) still fill the
+// block; every thread walks its rows four at a time with independent accumulators (the loads of a warp are
+// consecutive floats of one draw: coalesced), partial sums are combined through shared memory in slice order
+// (deterministic).
+constexpr int kSummaryThreads = 256;
+
+struct SumAcc {
+    double a, b, c, d;   // coordinate: (s1, s2, -, -); beta: (s1, s2, count, included sum); scalar: (v, -, -, -)
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256) summary_kernel(int C, int K, int D, const int* __restrict__ refs, int S,
-                                                      int skip, const T* __restrict__ draws,
-                                                      const T* __restrict__ stats, double* __restrict__ summary) {
+__global__ void __launch_bounds__(kSummaryThreads) summary_kernel(int C, int K, int D, const int* __restrict__ refs, int S,
+                                                                  int skip, const T* __restrict__ draws,
+                                                                  const T* __restrict__ stats, double* __restrict__ summary) {
+    extern __shared__ __align__(16) unsigned char summary_smem[];
+    SumAcc* part = reinterpret_cast<SumAcc*>(summary_smem);   // [n_slices][n_tasks]
     const int chain = blockIdx.x;
     const int b = chain / C;
     const int K1 = K - 1, DK1 = D * K1, P = D + 2 * DK1 + K, DK = D * K;
+    const int n_tasks = P + DK + SCCODA_NSUM_SCALAR;
+    const int n_slices = n_tasks >= kSummaryThreads ? 1 : kSummaryThreads / n_tasks;
     const int ref = refs[b];
     const T* dr = draws + (size_t)chain * S * P;
     const T* st = stats + (size_t)chain * S * SCCODA_NSTAT;
     double* out = summary + (size_t)chain * (SCCODA_NSUM_PARAM * P + SCCODA_NSUM_BETA * DK + SCCODA_NSUM_SCALAR);
     const int n_used = S - skip;
 
-    for (int task = threadIdx.x; task < P + DK + SCCODA_NSUM_SCALAR; task += blockDim.x) {
-        if (task < P) {
-            // mean and M2 of one state coordinate (shifted sums in fp64)
-            const double x0 = n_used > 0 ? (double)dr[(size_t)skip * P + task] : 0.0;
-            double s1 = 0.0, s2 = 0.0;
-            for (int r = skip; r < S; ++r) {
-                const double v = (double)dr[(size_t)r * P + task] - x0;
-                s1 += v;
-                s2 += v * v;
-            }
-            const double mean = n_used > 0 ? s1 / n_used : 0.0;
-            out[task] = x0 + mean;
-            out[P + task] = s2 - s1 * mean;
-        } else if (task < P + DK) {
-            // beta_dk = sigmoid(50 ind_raw) * sigma_d * b_offset, zero at the reference column
-            const int e = task - P;
-            const int d = e / K, k = e - d * K;
-            double cnt = 0.0, sinc = 0.0, s1 = 0.0, s2 = 0.0;
-            if (k != ref) {
-                const int j = k - (k > ref);
-                const int i_sig = d, i_off = D + d * K1 + j, i_raw = D + DK1 + d * K1 + j;
-                for (int r = skip; r < S; ++r) {
-                    const T* row = dr + (size_t)r * P;
-                    const T ind = sigmoid_stable(T(50) * row[i_raw]);
-                    const double beta = (double)(ind * (row[i_sig] * row[i_off]));
-                    if (fabs(beta) > 1e-3) {  // result_classes.py:249
-                        cnt += 1.0;
-                        sinc += beta;
+    for (int task0 = 0; task0 < n_tasks; task0 += kSummaryThreads) {
+        const int slice = n_slices > 1 ? (int)threadIdx.x / n_tasks : 0;
+        const int task = task0 + (n_slices > 1 ? (int)threadIdx.x - slice * n_tasks : (int)threadIdx.x);
+        const bool live = task < n_tasks && slice < n_slices;
+        SumAcc acc = {0.0, 0.0, 0.0, 0.0};
+        if (live) {
+            // rows of this slice: posterior tasks walk [skip, S), the statistics of the whole trace walk [0, S)
+            const bool post = task < P + DK;
+            const int lo_all = post ? skip : 0, n_all = S - lo_all;
+            const int per = (n_all + n_slices - 1) / n_slices;
+            const int r0 = lo_all + slice * per, r1 = min(S, r0 + per);
+            if (task < P) {
+                // mean and M2 of one state coordinate (sums shifted by the first used draw, fp64)
+                const double x0 = n_used > 0 ? (double)dr[(size_t)skip * P + task] : 0.0;
+                double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+                int r = r0;
+                for (; r + 3 < r1; r += 4) {
+                    T v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = dr[(size_t)(r + j) * P + task];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double w = (double)v[j] - x0;
+                        s1[j] += w;
+                        s2[j] = fma(w, w, s2[j]);
                     }
-                    s1 += beta;
-                    s2 += beta * beta;
+                }
+                for (; r < r1; ++r) {
+                    const double w = (double)dr[(size_t)r * P + task] - x0;
+                    s1[0] += w;
+                    s2[0] = fma(w, w, s2[0]);
+                }
+                acc.a = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+                acc.b = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+            } else if (post) {
+                // beta_dk = sigmoid(50 ind_raw) * sigma_d * b_offset, zero at the reference column
+                const int e = task - P;
+                const int d = e / K, k = e - d * K;
+                if (k != ref) {
+                    const int j = k - (k > ref);
+                    const int i_sig = d, i_off = D + d * K1 + j, i_raw = D + DK1 + d * K1 + j;
+#pragma unroll 4
+                    for (int r = r0; r < r1; ++r) {
+                        const T* row = dr + (size_t)r * P;
+                        const T ind = sigmoid_stable(T(50) * row[i_raw]);
+                        const double beta = (double)(ind * (row[i_sig] * row[i_off]));
+                        if (fabs(beta) > 1e-3) {  // result_classes.py:249
+                            acc.c += 1.0;
+                            acc.d += beta;
+                        }
+                        acc.a += beta;
+                        acc.b = fma(beta, beta, acc.b);
+                    }
+                }
+            } else {
+                const int q = task - P - DK;
+                if (q >= 1 && q <= 4) {
+#pragma unroll 4
+                    for (int r = r0; r < r1; ++r) {
+                        const T* row = st + (size_t)r * SCCODA_NSTAT;
+                        if (q == 1) acc.a += (double)row[SCCODA_ST_IS_ACCEPTED];
+                        else if (q == 2) acc.a += exp(fmin((double)row[SCCODA_ST_LOG_ACCEPT_RATIO], 0.0));
+                        else if (q == 3) acc.a += (double)row[SCCODA_ST_LEAPFROGS_TAKEN];
+                        else acc.a += (double)row[SCCODA_ST_DIVERGING];
+                    }
                 }
             }
-            const double mean = n_used > 0 ? s1 / n_used : 0.0;
-            double* ob = out + SCCODA_NSUM_PARAM * P;
-            ob[e] = cnt;
-            ob[DK + e] = sinc;
-            ob[2 * DK + e] = mean;
-            ob[3 * DK + e] = s2 - s1 * mean;
-        } else {
-            const int q = task - P - DK;
-            double v = 0.0;
-            if (q == 0) v = (double)n_used;
-            else if (q == 5) v = S > 0 ? (double)st[(size_t)(S - 1) * SCCODA_NSTAT + SCCODA_ST_STEP_SIZE] : 0.0;
-            else {
-                for (int r = 0; r < S; ++r) {
-                    const T* row = st + (size_t)r * SCCODA_NSTAT;
-                    if (q == 1) v += (double)row[SCCODA_ST_IS_ACCEPTED];
-                    else if (q == 2) v += exp(fmin((double)row[SCCODA_ST_LOG_ACCEPT_RATIO], 0.0));
-                    else if (q == 3) v += (double)row[SCCODA_ST_LEAPFROGS_TAKEN];
-                    else v += (double)row[SCCODA_ST_DIVERGING];
-                }
-            }
-            out[SCCODA_NSUM_PARAM * P + SCCODA_NSUM_BETA * DK + q] = v;
+            if (n_slices > 1) part[slice * n_tasks + task] = acc;
         }
+        __syncthreads();
+        if (live && slice == 0) {
+            for (int sl = 1; sl < n_slices; ++sl) {
+                const SumAcc o = part[sl * n_tasks + task];
+                acc.a += o.a; acc.b += o.b; acc.c += o.c; acc.d += o.d;
+            }
+            if (task < P) {
+                const double x0 = n_used > 0 ? (double)dr[(size_t)skip * P + task] : 0.0;
+                const double mean = n_used > 0 ? acc.a / n_used : 0.0;
+                out[task] = x0 + mean;
+                out[P + task] = acc.b - acc.a * mean;
+            } else if (task < P + DK) {
+                const int e = task - P;
+                const double mean = n_used > 0 ? acc.a / n_used : 0.0;
+                double* ob = out + SCCODA_NSUM_PARAM * P;
+                ob[e] = acc.c;
+                ob[DK + e] = acc.d;
+                ob[2 * DK + e] = mean;
+                ob[3 * DK + e] = acc.b - acc.a * mean;
+            } else {
+                const int q = task - P - DK;
+                double v = acc.a;
+                if (q == 0) v = (double)n_used;
+                else if (q == 5) v = S > 0 ? (double)st[(size_t)(S - 1) * SCCODA_NSTAT + SCCODA_ST_STEP_SIZE] : 0.0;
+                out[SCCODA_NSUM_PARAM * P + SCCODA_NSUM_BETA * DK + q] = v;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -87,11 +144,14 @@ cudaError_t launch_summary(int dtype, int B, int C, int N, int K, int D, const i
                            const void* draws, const void* stats, double* summary, cudaStream_t st) {
     (void)N;
     const int grid = B * C;
+    const int P = D + 2 * D * (K - 1) + K, n_tasks = P + D * K + SCCODA_NSUM_SCALAR;
+    const int n_slices = n_tasks >= kSummaryThreads ? 1 : kSummaryThreads / n_tasks;
+    const size_t smem = n_slices > 1 ? sizeof(SumAcc) * (size_t)n_slices * n_tasks : 0;   // partial sums [n_slices][n_tasks]
     if (dtype == SCCODA_F64)
-        summary_kernel<double><<<grid, 256, 0, st>>>(C, K, D, ref, num_results, skip, static_cast<const double*>(draws),
+        summary_kernel<double><<<grid, kSummaryThreads, smem, st>>>(C, K, D, ref, num_results, skip, static_cast<const double*>(draws),
                                                      static_cast<const double*>(stats), summary);
     else
-        summary_kernel<float><<<grid, 256, 0, st>>>(C, K, D, ref, num_results, skip, static_cast<const float*>(draws),
+        summary_kernel<float><<<grid, kSummaryThreads, smem, st>>>(C, K, D, ref, num_results, skip, static_cast<const float*>(draws),
                                                     static_cast<const float*>(stats), summary);
     return cudaGetLastError();
 }
