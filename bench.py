@@ -195,6 +195,17 @@ PACKED_DEVICE_FIELDS = ("ey", "eycst", "eidx", "colperm", "nbig", "ntot", "xu", 
                         "NI", "iy", "ipair", "ipos", "pcoef", "NG", "oy", "opair", "opos", "odesc")
 
 
+def traffic_from_profile(kernel_kind, a):
+    """dram__bytes_read + dram__bytes_write of the sampler launch from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json); only valid for the default workload and the kernel it was taken on."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if kernel_kind != 3 or (a.num_results, a.num_burnin, a.datasets, a.chains, a.K, a.n_per_group) != (20000, 5000, 1024, 4, 20, 10) or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "unit": "B per launch", "source": t["source"]}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -324,7 +335,7 @@ def run_ours(a):
     peaks, peak_kind = measured_peaks()
     draw_bytes = float(B) * C * a.num_results * (P + nat.NSTAT) * 4
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+                "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None, "traffic": traffic_from_profile(out.kernel_kind, a),
                 "peak_source": "FFMA micro-kernel measured in this run on this device (sccoda_measure_peaks); "
                                "MEASURED_PEAKS.json has no fp32 entry",
                 "mufu_peak_tops": mufu_peak, "kernel": {1: "hmc_kernel<float,W,grouped>", 3: "hmc_cc_kernel"}.get(out.kernel_kind, "hmc_kernel"), "kernel_ms": k_ms,
