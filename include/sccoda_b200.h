@@ -30,7 +30,9 @@
  *   eycst   [B,N*K]     per-count constant: fp32 -> r(y) if y>=6 else lgamma(y); fp64 -> 0   (see csrc/special.cuh)
  *   eidx    [B,N*K] u32 packed index (u*K + k) | (n << 16): covariate group u, ORIGINAL cell type k, row n
  *   colperm [B,K] i32   sorted column position kk -> original cell type k
- *   nbig    [B] i32     the first nbig elements have counts >= 6 (N * number of columns whose minimum is >= 6)
+ *   nbig    [B] i32     the first nbig elements have counts >= 6 (N * number of columns whose minimum is >= 6).
+ *                       With grouped != 0 only the value pass walks the list and the order is free: the packer then
+ *                       lists ALL counts >= 6 first (stable) and nbig counts them.
  *   ntot    [B,N]       row sums of y (scCODA_model.py:99-100)
  *   xu      [B,Umax,D]  unique covariate rows (design matrix without intercept, comp_ana.py:73-75)
  *   grp     [B,N] i32   covariate group of each row, non-decreasing

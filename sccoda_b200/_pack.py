@@ -253,6 +253,13 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
     it = build_items(ys, ntot, rstart, U, Umax)
     if grouped is None:
         grouped = bool(ITEM_R * int(it["NI"].max()) <= 1.6 * N * (K + 1))
+    if grouped:
+        # The pair/item gradient does not walk the element list; only the value pass does, and it does not care
+        # about the order.  List the counts >= 6 first (stable), so that the fast loop covers all of them and not
+        # just the columns without a small count.
+        order = np.argsort(ey < 6.0, axis=1, kind="stable")
+        ey, eycst, eidx = (np.take_along_axis(a, order, axis=1) for a in (ey, eycst, eidx))
+        nbig = (ey >= 6.0).sum(axis=1).astype(np.int32)
     return PackedProblem(grouped=int(bool(grouped)), NImax=it["NImax"], NOmax=it["NOmax"], NGmax=it["NGmax"],
                          NF=it["NF"], NT=it["NT"], NOT=it["NOT"], NI=it["NI"], NG=it["NG"], iy=np.ascontiguousarray(it["iy"], dtype),
                          ipair=it["ipair"], ipos=it["ipos"], pcoef=np.ascontiguousarray(it["pcoef"], dtype),

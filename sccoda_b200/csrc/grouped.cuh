@@ -245,8 +245,17 @@ __device__ __forceinline__ void dm_grad_items(const Dims& dm, const DataTile<T>&
         }
     }
     g.sync();
-    // ---- C: one column per thread: G_uk = c_uk (Br_uk - Br_total(u)), column sums over the groups, chain rule
-    //         (SURVEY §8a), sigma_d by a group reduction.  Covariates are taken four at a time.
+    // ---- P2: one pair per thread: G_uk = c_uk (Br_uk - Br_total(u)), parked in the (no longer needed) rational slot
+#pragma unroll 1
+    for (int p = tid; p < U * K; p += TS) {
+        const int pt = tot0 + fast_div(p, dm.magicK);
+        const T bt = pair_bracket<T>(prec[pt].rat, A + pt * NF, NF);
+        const PairRec<T> r = prec[p];
+        prec[p].rat = r.c * (pair_bracket<T>(r.rat, A + p * NF, NF) - bt);
+    }
+    g.sync();
+    // ---- C: one column per thread: column sums over the groups, chain rule, sigma_d by a group
+    //         reduction.  Covariates are taken four at a time.
 #pragma unroll 1
     for (int d0 = 0; d0 < D; d0 += 4) {
         T part[4] = {T(0), T(0), T(0), T(0)};
@@ -259,10 +268,7 @@ __device__ __forceinline__ void dm_grad_items(const Dims& dm, const DataTile<T>&
             T acc[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll 1
             for (int u = 0; u < U; ++u) {
-                const int pt = tot0 + u, p = u * K + kc;
-                const T bt = pair_bracket<T>(prec[pt].rat, A + pt * NF, NF);    // uniform over the group
-                const PairRec<T> r = prec[p];
-                const T G = r.c * (pair_bracket<T>(r.rat, A + p * NF, NF) - bt);
+                const T G = prec[u * K + kc].rat;
                 g0 += G;
 #pragma unroll
                 for (int dd = 0; dd < 4; ++dd)

@@ -61,7 +61,7 @@ struct KArgs {
 __host__ __device__ inline size_t rnd16(size_t bytes) { return (bytes + 15) & ~size_t(15); }
 
 struct SmemPlan {
-    size_t ntot, xu, grp, rstart, colperm, el, pcoef, iy, ipair, ipos, data_total;    // per CTA
+    size_t ntot, xu, grp, rstart, colperm, el, eyc, pcoef, iy, ipair, ipos, data_total;   // per CTA
     size_t red, cp, rowterm, G, Gu, beta, ind, gk, vec, chain_total;                  // per chain (relative)
 };
 
@@ -83,6 +83,7 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
     p.rstart = o; o += rnd16((size_t)(Umax + 1) * 4);
     p.colperm = o; o += rnd16((size_t)K * 4);
     p.el = o; o += el_smem ? rnd16(NK * 2 * ts) : 0;
+    p.eyc = o; o += el_smem ? rnd16(NK * ts) : 0;
     p.pcoef = o; o += grouped ? rnd16(NP * 6 * ts) : 0;
     p.iy = o; o += grouped ? rnd16((size_t)kItemR * nimax * ts) : 0;
     p.ipair = o; o += grouped ? rnd16((size_t)nimax * 2) : 0;

@@ -37,7 +37,7 @@ template <typename T>
 __device__ __forceinline__ void stage_dataset(const KArgs& a, int b, const SmemPlan& pl, DataTile<T>& dt) {
     const int N = a.dm.N, K = a.dm.K, D = a.dm.D, Umax = a.Umax, NK = a.dm.NK;
     dt.ntot = (uint32_t)pl.ntot; dt.xu = (uint32_t)pl.xu; dt.grp = (uint32_t)pl.grp; dt.rstart = (uint32_t)pl.rstart;
-    dt.colperm = (uint32_t)pl.colperm; dt.el = (uint32_t)pl.el;
+    dt.colperm = (uint32_t)pl.colperm; dt.el = (uint32_t)pl.el; dt.eyc = (uint32_t)pl.eyc;
     dt.el_smem = a.el_smem;
     dt.ey = static_cast<const T*>(a.ey) + (size_t)b * NK;
     dt.eidx = a.eidx + (size_t)b * NK;
@@ -55,6 +55,7 @@ __device__ __forceinline__ void stage_dataset(const KArgs& a, int b, const SmemP
             v.idx = dt.eidx[e];
             el[e] = v;
         }
+        copy_to_smem(sp<T>(dt.eyc), dt.eycst, NK);
     }
     dt.nbig = a.nbig[b];
     dt.U = a.U[b];

@@ -75,6 +75,7 @@ struct DataTile {
     const T* ey;           // global [NK]
     const uint32_t* eidx;  // global [NK]
     const T* eycst;        // global [NK] host constants of the value pass
+    uint32_t eyc;          // smem T[NK] copy of eycst (only when el_smem)
     int U, ref;
     int nbig;              // elements [0, nbig) have counts >= 6
     double lconst;         // all theta-independent terms of the log-density (host, fp64)
@@ -127,9 +128,10 @@ struct Group {
             sync();  // previous consumers of red are done
             if ((tid & 31) == 0) r[tid >> 5] = v;
             sync();
-            v = r[0];
+            // second stage as a tree over the W warp sums (a serial walk costs W dependent shared-memory loads)
+            v = r[tid & (W - 1)];
 #pragma unroll
-            for (int w = 1; w < W; ++w) v += r[w];
+            for (int o = W >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         }
         return v;
     }
@@ -489,6 +491,17 @@ __device__ __noinline__ double value_joint_fixup(const Dims& dm, const DataTile<
                                                  int tid) {
     constexpr int TS = Group<W>::SIZE;
     double fix = 0.0;
+    if (dt.el_smem) {
+        const Elem<T>* el = sp<Elem<T>>(dt.el);
+        const T* eyc = sp<T>(dt.eyc);
+#pragma unroll 1
+        for (int e = tid; e < dm.NK; e += TS) {
+            const Elem<T> v = el[e];
+            const T c = cp[v.idx & 0xffffu].c;
+            if (c >= c_joint) fix += (double)lgamma_joint(c, v.y, eyc[e]) - (double)lgamma_shift(c, v.y, eyc[e]);
+        }
+        return fix;
+    }
 #pragma unroll 1
     for (int e = tid; e < dm.NK; e += TS) {
         const uint32_t ix = dt.eidx[e];
@@ -591,23 +604,31 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
         T acc = T(0);
         if (dt.el_smem) {
             const Elem<T>* el = sp<Elem<T>>(dt.el);
+            const T* eyc = sp<T>(dt.eyc);
 #pragma unroll 2
             for (int e = tid; e < dt.nbig; e += TS) {
                 const Elem<T> v = el[e];
-                acc += lgamma_shift_big(cp[v.idx & 0xffffu].c, v.y, dt.eycst[e]);
+                acc += lgamma_shift_big(cp[v.idx & 0xffffu].c, v.y, eyc[e]);
             }
 #pragma unroll 1
             for (int e = dt.nbig + tid; e < dm.NK; e += TS) {
                 const Elem<T> v = el[e];
-                acc += lgamma_shift(cp[v.idx & 0xffffu].c, v.y, dt.eycst[e]);   // mixed columns: branch on y
+                acc += lgamma_shift(cp[v.idx & 0xffffu].c, v.y, eyc[e]);   // mixed columns: branch on y
             }
             lp += (double)acc;
         } else {
+            // element list streamed from global memory (tiles too large for shared memory, fp64 parity build): same
+            // split into counts >= 6 and mixed columns, four independent loads in flight per thread
+            const T* __restrict__ ey = dt.ey;
+            const T* __restrict__ eyc = dt.eycst;
+            const uint32_t* __restrict__ eidx = dt.eidx;
+#pragma unroll 8
+            for (int e = tid; e < dt.nbig; e += TS)
+                acc += lgamma_shift_big(cp[__ldg(eidx + e) & 0xffffu].c, __ldg(ey + e), sizeof(T) == 4 ? __ldg(eyc + e) : T(0));
 #pragma unroll 1
-            for (int e = tid; e < dm.NK; e += TS) {
-                const uint32_t ix = dt.eidx[e];
-                lp += (double)lgamma_shift(cp[ix & 0xffffu].c, dt.ey[e], sizeof(T) == 4 ? dt.eycst[e] : T(0));
-            }
+            for (int e = dt.nbig + tid; e < dm.NK; e += TS)
+                acc += lgamma_shift(cp[__ldg(eidx + e) & 0xffffu].c, __ldg(ey + e), sizeof(T) == 4 ? __ldg(eyc + e) : T(0));
+            lp += (double)acc;
         }
     }
     // every thread owns a different slice of the elements in the fix-up: the flag must be uniform over the group

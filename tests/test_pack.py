@@ -53,7 +53,7 @@ def test_element_list_layout():
     x, y = synthetic_dataset(4, N=8, K=6)
     y[3, 2] = 0          # column 2 becomes a small-count column
     y[:, 5] = 2          # column 5 too
-    pk = pack(x, y, 0, dtype=np.float64)
+    pk = pack(x, y, 0, dtype=np.float64, grouped=False)
     N, K = 8, 6
     ys, grp = pk.y[0], pk.grp[0]
     colmin = ys.min(axis=0)
@@ -66,6 +66,12 @@ def test_element_list_layout():
         assert pk.ey[0][e] == ys[n, k]
         assert pk.eidx[0][e] == (grp[n] * K + k) | (n << 16)
     assert np.all(pk.ey[0][:pk.nbig[0]] >= 6)
+    # grouped layout: the gradient no longer walks the list, so every count >= 6 is listed first (stable partition)
+    pg = pack(x, y, 0, dtype=np.float64, grouped=True)
+    assert pg.nbig[0] == (ys >= 6).sum() > pk.nbig[0]
+    assert np.all(pg.ey[0][:pg.nbig[0]] >= 6) and np.all(pg.ey[0][pg.nbig[0]:] < 6)
+    key = lambda p: sorted(zip(p.eidx[0].tolist(), p.ey[0].tolist(), p.eycst[0].tolist()))
+    assert key(pg) == key(pk)                                     # same multiset of (index, count, constant) records
 
 
 def test_continuous_covariates_have_one_group_per_row():

@@ -1,5 +1,5 @@
-# A/B timing at the benchmark shape (run on the GPU box)
+# A/B at the shape of BASELINE config 3 with a fixed amount of work (HMC, L=10, 64 chains x 16 warps)
 for i in 1 2; do
-python tools/prof_hmc.py --results 400 --burnin 100 --grouped 1
+SCCODA_B200_LIB=$PWD/sccoda_b200/libA.so python tools/prof_nuts.py --method 0 --results 300 --burnin 100 | sed 's/^/A /'
+python tools/prof_nuts.py --method 0 --results 300 --burnin 100 | sed 's/^/B /'
 done
-python tools/prof_hmc.py --results 2000 --burnin 500 --grouped 1
