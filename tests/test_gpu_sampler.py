@@ -176,6 +176,74 @@ def test_case_control_kernel_follows_generic_kernel(method):
     assert many.launches > 1 and np.array_equal(many.draws.cpu().numpy(), d1)
 
 
+def _cc_vs_oracle(xs, ys, refs, C=2, steps=12, seed=4):
+    """Run the case/control kernel and the generic kernel on a batch; return both outputs and the packed problem."""
+    from oracle import np_oracle as o
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    B, K = len(xs), ys[0].shape[1]
+    pk = pack(np.stack(xs), np.stack(ys), np.asarray(refs), dtype=np.float32, grouped=True)
+    prob = DeviceProblem(pk, chains=C)
+    init = _init(np.random.RandomState(seed), 1, K, B * C).reshape(B, C, -1) * 0.5
+    init[..., 0] = 1.0
+    outs = [prob.sample(init, prob.make_sampler(0, steps, 0, num_adapt=steps, seed=seed, warps_per_chain=1,
+                                                generic_only=g)) for g in (True, False)]
+    assert outs[0].kernel_kind == 1 and outs[1].kernel_kind == 3
+    d = outs[1].draws.double().cpu().numpy()
+    lp = outs[1].stat("target_log_prob").double().cpu().numpy()
+    assert np.isfinite(d).all() and np.isfinite(lp).all()
+    for b in range(B):
+        m = o.prepare(xs[b], ys[b], int(refs[b]))
+        for c in range(C):
+            ref = np.array([o.logp(d[b, c, i], m) for i in range(steps)])
+            assert np.abs(lp[b, c] - ref).max() < 5e-6 * np.abs(ref).max() + 4e-3, (b, c, np.abs(lp[b, c] - ref).max())
+    n = min(steps, 5)
+    assert np.abs(outs[0].draws.cpu().numpy()[:, :, :n] - outs[1].draws.cpu().numpy()[:, :, :n]).max() < 2e-3
+    return outs, pk
+
+
+@pytest.mark.parametrize("K", [2, 3, 31])
+def test_case_control_kernel_cell_type_range(K):
+    """Smallest and largest number of cell types the lane-per-cell-type kernel takes (K = 32 goes to the generic one)."""
+    xs, ys = zip(*[synthetic_dataset(60 + b, N=10, K=K) for b in range(2)])
+    _cc_vs_oracle(xs, ys, [K - 1, 0])
+
+
+def test_case_control_kernel_k32_falls_back_to_generic():
+    from sccoda_b200.engine import DeviceProblem
+    x, y = synthetic_dataset(3, N=10, K=32)
+    prob = DeviceProblem.from_arrays(x, y, 31, chains=2, dtype=np.float32, grouped=True)
+    out = prob.sample(_init(np.random.RandomState(0), 1, 32, 2)[None] * 0.5,
+                      prob.make_sampler(0, 6, 0, num_adapt=6, seed=1, warps_per_chain=1))
+    assert out.kernel_kind == 1 and np.isfinite(out.draws.cpu().numpy()).all()
+
+
+def test_case_control_kernel_ragged_batches():
+    """Datasets of one batch that differ in what the kernel's loops see: many rows per group (several items per pair),
+    a dataset whose rows all share one covariate value (one group), a dataset of small counts only (no items at all for
+    most pairs), pseudocounts and non-integer counts (odd counts), unbalanced groups."""
+    rs = np.random.RandomState(3)
+    N, K = 33, 7
+    xs, ys = [], []
+    for b in range(5):
+        x, y = synthetic_dataset(70 + b, N=N, K=K)
+        if b == 0:
+            x[:] = 0.0
+            x[-4:] = 1.0                                   # 29 + 4 rows: six items for the big group
+        if b == 1:
+            x[:] = 1.0                                     # a single covariate group
+        if b == 2:
+            y = rs.randint(0, 6, size=(N, K)).astype(float)            # counts 0..5 only (0 -> pseudocount)
+            y[:, 0] += 1
+        if b == 3:
+            y[rs.rand(N, K) < 0.2] = 0.0
+            y[5, 3], y[6, 3], y[7, 4] = 2.5, 0.25, 5.75
+        xs.append(x)
+        ys.append(y)
+    outs, pk = _cc_vs_oracle(xs, ys, [6, 0, 3, 2, 5], C=3, steps=10)
+    assert pk.NT >= 6 and pk.NOT >= 2 and int(pk.U.min()) == 1 and int(pk.U.max()) == 2
+
+
 def test_fp32_statistical_parity_nuts():
     from sccoda_b200.engine import DeviceProblem
     x, y, _ = haber_salm()
