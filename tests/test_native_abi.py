@@ -71,10 +71,19 @@ def test_launch_plan_scales_warps_for_few_chains_and_big_models():
     pk = pack(x, y, 49)
     rc, w, cpc, grid, smem = _plan(_problem(pk, 64), _sampler(method=2))
     assert rc == 0 and w == 16 and cpc == 1 and grid == 64 and smem <= 227 * 1024
+    # a single chain of a small case/control problem: the lane-per-cell-type kernel (one warp) ...
     x, y = synthetic_dataset(0, N=10, K=5)
     pk = pack(x, y, 4)
     rc, w, cpc, grid, smem = _plan(_problem(pk, 1), _sampler())
-    assert rc == 0 and w == 2 and grid == 1
+    assert rc == 0 and w == 1 and grid == 1 and pk.grouped == 1
+    kind = ctypes.c_int32()
+    assert nat.lib().sccoda_kernel_kind(ctypes.byref(_problem(pk, 1)), ctypes.byref(_sampler()), ctypes.byref(kind)) == 0
+    assert kind.value == 3
+    # ... but several warps per chain for NUTS, for the fp64 build and when the sampler asks for the generic kernel
+    rc, w, *_ = _plan(_problem(pk, 1), _sampler(method=2))
+    assert rc == 0 and w == 2
+    rc, w, *_ = _plan(_problem(pk, 1), _sampler(generic_only=1))
+    assert rc == 0 and w == 2
 
 
 @pytest.mark.parametrize("kw,code", [(dict(method=7), -11), (dict(num_results=0), -12), (dict(num_leapfrog=0), -13),
