@@ -203,7 +203,11 @@ def traffic_from_profile(kernel_kind, a):
         return None
     with open(p) as f:
         t = json.load(f)
-    return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "unit": "B per launch", "source": t["source"]}
+    return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "unit": "B per launch", "source": t["source"],
+            "ncu_pipes_pct": {"fma_cycles_active": t.get("sm__pipe_fma_cycles_active_pct"),
+                              "fma_inst_executed": t.get("sm__inst_executed_pipe_fma_pct"),
+                              "xu_inst_executed": t.get("sm__inst_executed_pipe_xu_pct"),
+                              "issue_active": t.get("smsp__issue_active_pct")}}
 
 
 def measured_peaks():
