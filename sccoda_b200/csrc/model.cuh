@@ -208,12 +208,7 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
         }
     }
     // ---- F2 + F3
-#ifdef SCCODA_ABLATE_F
-    if (false) {
-    } else if (false) {
-#else
     if (W == 1 && U <= 32) {
-#endif
         // few covariate groups, one warp: S_u by warp shuffles while the concentrations are produced
 #pragma unroll 1
         for (int u = 0; u < U; ++u) {
@@ -272,11 +267,7 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     g.sync();
 
     // ---- E: elements  G = c (digamma(c+y) - digamma(c) - rowterm_n)
-#ifdef SCCODA_ABLATE_E
-    if (false) {
-#else
     if (dt.el_smem) {
-#endif
         const Elem<T>* el = sp<Elem<T>>(dt.el);
         // counts >= 6, no recurrence shift needed.  Full batches of EB elements per thread are written
         // loads-first / stores-last: the arrays share one shared-memory buffer, so the compiler would otherwise
@@ -316,11 +307,7 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     } else {
         // element list streamed from global memory (fp64 parity build, or tiles too large for shared memory)
 #pragma unroll 1
-#ifdef SCCODA_ABLATE_E
-        for (int e = tid; e < 0; e += TS) {
-#else
         for (int e = tid; e < dm.NK; e += TS) {
-#endif
             const uint32_t ix = dt.eidx[e];
             const CPsi<T> q = cp[ix & 0xffffu];
             G[e] = q.c * (digamma_pos(q.c + dt.ey[e]) - q.psi - rowterm[ix >> 16]);
@@ -337,11 +324,7 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
         const int k = colperm[has ? tid : 0];
         T g0 = T(0);
         T acc[4] = {T(0), T(0), T(0), T(0)};
-#ifdef SCCODA_ABLATE_B
-        if (false) {
-#else
         if (has) {
-#endif
             const T* p = G + tid * N;
             int n = 0;
 #pragma unroll 1
@@ -534,9 +517,6 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     const int* grp = sp<int>(dt.grp);
     const T* ntot = sp<T>(dt.ntot);
     double lp = 0.0;
-#ifdef SCCODA_ABLATE_VALUE
-    return g.sum(lp) + (double)sigma[0] * 1e-30;
-#endif
     // priors: HalfCauchy(0,1) on sigma_d (:703-707), Normal(0,1) on b_offset / ind_raw (:709-722), Normal(0,5) on
     // alpha (:736-741); the theta-independent constants live in dt.lconst
     {

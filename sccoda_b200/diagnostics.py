@@ -104,3 +104,24 @@ def rhat_from_moments(mean: torch.Tensor, m2: torch.Tensor, n: int) -> torch.Ten
     within = (m2 / (n - 1.0)).mean(dim=-2)
     between = mean.var(dim=-2, unbiased=True)
     return torch.sqrt(((n - 1.0) / n * within + between) / within)
+
+
+def hdi(x: torch.Tensor, prob: float = 0.94) -> torch.Tensor:
+    """Highest-density interval of the draws along the last dim, for every leading index at once: the shortest
+    interval that contains floor(prob * n) of the sorted non-NaN draws — what az.summary(kind="stats", skipna=True)
+    reports for a unimodal sample and what CAResult.summary_prepare reads (sccoda/util/result_classes.py:153-196;
+    NaN marks draws whose indicator is below 1e-3, :178).  Returns [..., 2] (NaN where no draw is valid)."""
+    v, _ = torch.sort(x, dim=-1)                                   # NaNs sort to the end
+    n = (~torch.isnan(x)).sum(dim=-1, keepdim=True)                # valid draws per row
+    k = torch.floor(prob * n.to(torch.float64)).to(torch.long)     # window length (in steps) per row
+    S = x.shape[-1]
+    pos = torch.arange(S, device=x.device).expand(x.shape)
+    hi_idx = torch.clamp(pos + k, max=S - 1)
+    width = torch.gather(v, -1, hi_idx) - v
+    width = torch.where(pos + k < n, width, torch.full_like(width, float("inf")))
+    best = torch.argmin(width, dim=-1, keepdim=True)
+    lo = torch.gather(v, -1, best)
+    hi = torch.gather(v, -1, torch.clamp(best + k, max=S - 1))
+    out = torch.cat([lo, hi], dim=-1)
+    empty = (n == 0) | (k >= n)
+    return torch.where(empty.expand_as(out), torch.full_like(out, float("nan")), out)

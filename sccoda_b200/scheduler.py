@@ -141,6 +141,7 @@ class SweepConfig:
     warps_per_chain: int = 0
     est_fdr: float = 0.05
     diag_datasets: int = 0      # rank-normalised R-hat / bulk ESS for the first n local datasets (0 = none)
+    hdi_prob: Optional[float] = None   # e.g. 0.94: HDIs of intercepts and effects for every dataset, on device
 
 
 @dataclass
@@ -213,6 +214,32 @@ def shard_results(sh: SweepShard, cfg: SweepConfig) -> Dict[str, "object"]:
             rh[b0:b1] = dg.rhat(coords)
         res["ess_bulk"] = ess
         res["rhat_rank"] = rh
+    if cfg.hdi_prob is not None:
+        # HDIs as CAResult.summary_prepare reports them (result_classes.py:153-196), chains pooled: intercepts over all
+        # retained draws, effects over b_raw * ind of the draws whose indicator is >= 1e-3 (NaN otherwise; the
+        # reference column reads 0).  Device sort, a block of datasets at a time.
+        skip = min(cfg.num_burnin, cfg.num_results)
+        a_hdi = torch.zeros((B, K, 2), dtype=torch.float64, device=sh.summary.device)
+        b_hdi = torch.zeros((B, D * K, 2), dtype=torch.float64, device=sh.summary.device)
+        ref = torch.as_tensor(prob.packed.ref, device=sh.summary.device).long()
+        nonref = torch.stack([torch.cat([torch.arange(0, int(r)), torch.arange(int(r) + 1, K)]) for r in prob.packed.ref]
+                             ).to(sh.summary.device)                                        # [B,K-1] cell type of effect j
+        blk = max(1, int(2 ** 27 // max(1, C * (cfg.num_results - skip) * (K + D * (K - 1)))))
+        for b0 in range(0, B, blk):
+            b1 = min(B, b0 + blk)
+            d = sh.out.draws[b0:b1, :, skip:, :].to(torch.float32)                          # [b,C,S,P]
+            nb_, S_ = d.shape[0], d.shape[2]
+            alpha = d[..., prob.P - K:].permute(0, 3, 1, 2).reshape(nb_, K, C * S_)
+            a_hdi[b0:b1] = dg.hdi(alpha, cfg.hdi_prob).double()
+            sig = d[..., :D].repeat_interleave(K - 1, dim=-1)
+            ind = torch.sigmoid(50.0 * d[..., D + D * (K - 1):D + 2 * D * (K - 1)])
+            eff = torch.where(ind >= 1e-3, sig * d[..., D:D + D * (K - 1)] * ind, torch.full_like(ind, float("nan")))
+            h = dg.hdi(eff.permute(0, 3, 1, 2).reshape(nb_, D * (K - 1), C * S_), cfg.hdi_prob).double()   # [b,D(K-1),2]
+            for dd in range(D):
+                idx = (dd * K + nonref[b0:b1])[:, :, None].expand(-1, -1, 2)
+                b_hdi[b0:b1].scatter_(1, idx, h[:, dd * (K - 1):(dd + 1) * (K - 1)])
+        res["alpha_hdi"] = a_hdi.reshape(B, K * 2)
+        res["effect_hdi"] = b_hdi.reshape(B, D * K * 2)
     return res
 
 

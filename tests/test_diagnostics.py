@@ -112,3 +112,26 @@ def test_rhat_from_moments():
     W = a.var(2, ddof=1).mean(1)
     Bn = mean.var(1, ddof=1)
     assert np.allclose(got, np.sqrt((499 / 500 * W + Bn) / W))
+
+
+def test_hdi_matches_arviz_definition_on_ragged_rows():
+    """Device HDI (torch) == the numpy restatement of az.hdi with skipna, including NaN-masked and empty rows."""
+    import torch
+    from oracle import np_oracle as o
+    from sccoda_b200 import diagnostics as dg
+    rs = np.random.RandomState(0)
+    x = rs.gamma(2.0, 1.0, size=(3, 5, 400))
+    x[0, 1, rs.rand(400) < 0.6] = np.nan
+    x[1, 2, :] = np.nan
+    x[2, 0, 1:] = np.nan                              # a single valid draw: no window fits
+    x[2, 3, :397] = np.nan                            # three valid draws
+    got = dg.hdi(torch.from_numpy(x), 0.94).numpy()
+    for i in range(3):
+        for j in range(5):
+            lo, hi = o.hdi(x[i, j], 0.94)
+            if np.isnan(lo):
+                assert np.isnan(got[i, j]).all()
+            else:
+                assert np.allclose(got[i, j], [lo, hi])
+    got90 = dg.hdi(torch.from_numpy(x[0, 0]), 0.9).numpy()
+    assert np.allclose(got90, o.hdi(x[0, 0], 0.9))

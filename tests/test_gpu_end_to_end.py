@@ -3,6 +3,7 @@ CompositionalAnalysis(...) -> sample_hmc / sample_hmc_da / sample_nuts -> CAResu
 import numpy as np
 import pytest
 
+from conftest import synthetic_dataset
 from sccoda_b200 import datasets
 from sccoda_b200.util import cell_composition_data as dat
 from sccoda_b200.util import comp_ana as mod
@@ -153,3 +154,33 @@ def test_sweep_inclusion_probabilities_and_credible_calls_match_oracle():
             assert abs(res["final_effect"][b, k] - final_o[b, k]) < 0.15
             assert res["final_effect"][b, k] > 0
     assert found >= 3
+
+
+def test_sweep_hdis_on_device_match_host_summary_logic():
+    """SweepConfig.hdi_prob: intercept and effect HDIs of every dataset from the device-resident draws, against the
+    numpy restatement of what CAResult.summary_prepare computes (result_classes.py:153-196) on the same draws."""
+    from oracle import np_oracle as o
+    from sccoda_b200 import scheduler as sch
+    B, C, K, nr, nb = 3, 2, 6, 900, 300
+    xs, ys = zip(*[synthetic_dataset(80 + b, N=12, K=K) for b in range(B)])
+    refs = np.array([5, 0, 2])
+    cfg = sch.SweepConfig(method=0, num_results=nr, num_burnin=nb, chains=C, seed=3, hdi_prob=0.94)
+    res, shard = sch.run_sweep(np.stack(xs), np.stack(ys), refs, cfg)
+    d = shard.out.draws.float().cpu().numpy()[:, :, nb:, :]                    # [B,C,S,P]
+    a_hdi = res["alpha_hdi"].reshape(B, K, 2)
+    e_hdi = res["effect_hdi"].reshape(B, K, 2)
+    for b in range(B):
+        pooled = d[b].reshape(-1, d.shape[-1])
+        for k in range(K):
+            assert np.allclose(a_hdi[b, k], o.hdi(pooled[:, -K + k].astype(np.float64), 0.94), atol=1e-6)
+        sig, boff, iraw = pooled[:, 0:1], pooled[:, 1:K], pooled[:, K:2 * K - 1]
+        ind = 1.0 / (1.0 + np.exp(-50.0 * iraw.astype(np.float64)))
+        eff = np.where(ind >= 1e-3, sig * boff * ind, np.nan)
+        j = 0
+        for k in range(K):
+            if k == refs[b]:
+                assert np.all(e_hdi[b, k] == 0.0)
+                continue
+            lo, hi = o.hdi(eff[:, j], 0.94)
+            assert np.allclose(e_hdi[b, k], [lo, hi], atol=2e-5, equal_nan=True), (b, k, e_hdi[b, k], lo, hi)
+            j += 1
