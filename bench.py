@@ -192,7 +192,7 @@ class ClockSampler:
 
 
 PACKED_DEVICE_FIELDS = ("ey", "eycst", "eidx", "colperm", "nbig", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst",
-                        "NI", "iy", "ipair", "ipos", "pcoef", "NG", "oy", "opair", "opos", "odesc")
+                        "NI", "iy", "ipair", "ipos", "inreal", "pcoef", "NG", "oy", "opair", "opos", "odesc")
 
 
 def traffic_from_profile(kernel_kind, a):

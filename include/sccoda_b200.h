@@ -51,6 +51,8 @@
  *   iy      [B,SCCODA_ITEM_R,NImax]  counts of the items (slot-major, so that consecutive items are contiguous)
  *   ipair   [B,NImax] u16    pair of each item
  *   ipos    [B,NImax] u16    result slot of each item
+ *   inreal  [B,NImax] u8     how many of the SCCODA_ITEM_R counts of the item are data (the value pass walks the items
+ *                            for the counts >= 6 and the tail [nbig, N*K) of the element list for the rest)
  *   pcoef   [B,NP,6]    numerators (a0,b0,a1,b1,a2,b2) of  sum_i W_i/(c+i) = (a0 c+b0)/(c(c+5)) + (a1 c+b1)/((c+1)(c+4))
  *                       + (a2 c+b2)/((c+2)(c+3)),  W_i = #counts>=6 + #odd + #{counts in {1..5} that exceed i}
  *   NG      [B] i32     number of odd groups of dataset b (<= NGmax)
@@ -126,6 +128,7 @@ typedef struct sccoda_problem {
     const void* iy;
     const uint16_t* ipair;
     const uint16_t* ipos;
+    const uint8_t* inreal;
     const void* pcoef;
     const int32_t* NG;
     const void* oy;

@@ -37,7 +37,7 @@ class Problem(ctypes.Structure):
                 ("grp", ctypes.c_void_p), ("rstart", ctypes.c_void_p), ("U", ctypes.c_void_p),
                 ("ref", ctypes.c_void_p), ("lconst", ctypes.c_void_p),
                 ("NI", ctypes.c_void_p), ("iy", ctypes.c_void_p), ("ipair", ctypes.c_void_p),
-                ("ipos", ctypes.c_void_p), ("pcoef", ctypes.c_void_p), ("NG", ctypes.c_void_p),
+                ("ipos", ctypes.c_void_p), ("inreal", ctypes.c_void_p), ("pcoef", ctypes.c_void_p), ("NG", ctypes.c_void_p),
                 ("oy", ctypes.c_void_p), ("opair", ctypes.c_void_p), ("opos", ctypes.c_void_p),
                 ("odesc", ctypes.c_void_p)]
 
@@ -45,7 +45,7 @@ class Problem(ctypes.Structure):
 def problem_fields(pk, ptr):
     """Keyword arguments of Problem(...) for a PackedProblem; ptr(array_or_tensor) -> address."""
     names = ("ey", "eycst", "eidx", "colperm", "nbig", "ntot", "xu", "grp", "rstart", "U", "ref", "lconst",
-             "NI", "iy", "ipair", "ipos", "pcoef", "NG", "oy", "opair", "opos", "odesc")
+             "NI", "iy", "ipair", "ipos", "inreal", "pcoef", "NG", "oy", "opair", "opos", "odesc")
     kw = dict(B=pk.B, N=pk.N, K=pk.K, D=pk.D, Umax=pk.Umax, dtype=F32 if pk.dtype.itemsize == 4 else F64,
               nbig_min=pk.nbig_min, grouped=pk.grouped, NImax=pk.NImax, NOmax=pk.NOmax, NGmax=pk.NGmax, NF=pk.NF, NT=pk.NT, NOT=pk.NOT)
     kw.update({n: ptr(n) for n in names})

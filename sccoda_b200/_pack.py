@@ -57,6 +57,7 @@ class PackedProblem:
     iy: np.ndarray = None            # [B,ITEM_R,NImax] counts >= 6 of each item, padded with 6
     ipair: np.ndarray = None         # [B,NImax] uint16 pair of each item
     ipos: np.ndarray = None          # [B,NImax] uint16 result slot of each item: pair*NF + t
+    inreal: np.ndarray = None        # [B,NImax] uint8 counts of the item that are data (the rest is padding)
     pcoef: np.ndarray = None         # [B,NP,6] rational coefficients of each pair, NP = Umax*(K+1)
     oy: np.ndarray = None            # [B,NOmax] counts < 6 that are not in {0,1,...,5}
     opair: np.ndarray = None         # [B,NGmax] uint16 pair of each odd group
@@ -108,7 +109,7 @@ def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndar
     nslot_max = 1
     nt_max, not_max = 1, 0
     for b in range(B):
-        yb, pb, tb, ob, opb, otb, odb = [], [], [], [], [], [], []
+        yb, pb, tb, rb, ob, opb, otb, odb = [], [], [], [], [], [], [], []
         n_odd = 0
         for u in range(int(U[b])):
             blk = ext[b, rstart[b, u]:rstart[b, u + 1]]                       # [cnt,K+1]
@@ -137,6 +138,7 @@ def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndar
                 yb.append(chunks[tt, :, cc])
                 pb.append(pair[cc])
                 tb.append(tt)
+                rb.append(np.minimum(R, nb[cc] - R * tt))                     # real (non-padding) counts of the item
             if no.any():
                 rr, cc = np.nonzero(odd.T)                                    # rr = column, cc = row (column-major)
                 ob.append(blk[cc, rr])
@@ -148,7 +150,7 @@ def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndar
         cat = lambda lst, shape, dt: np.concatenate(lst).astype(dt) if lst else np.zeros(shape, dt)
         per_ds.append((cat(yb, (0, R), np.float64), cat(pb, (0,), np.int64), cat(tb, (0,), np.int64),
                        cat(ob, (0,), np.float64), cat(opb, (0,), np.int64), cat(otb, (0,), np.int64),
-                       cat(odb, (0,), np.int64)))
+                       cat(odb, (0,), np.int64), cat(rb, (0,), np.int64)))
     NF = 2
     while NF < nslot_max:
         NF *= 2
@@ -167,16 +169,18 @@ def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndar
     opair = np.zeros((B, NGmax), dtype=np.uint16)
     opos = np.full((B, NGmax), NP * NF, dtype=np.uint16)
     odesc = np.zeros((B, NGmax), dtype=np.uint32)
-    for b, (yb, pb, tb, ob, opb, otb, odb) in enumerate(per_ds):
+    inreal = np.zeros((B, NImax), dtype=np.uint8)
+    for b, (yb, pb, tb, ob, opb, otb, odb, rb) in enumerate(per_ds):
         iy[b, :, :NI[b]] = yb.T
         ipair[b, :NI[b]] = pb
+        inreal[b, :NI[b]] = rb
         ipos[b, :NI[b]] = pb * NF + tb
         oy[b, :ob.size] = ob
         opair[b, :NG[b]] = opb
         opos[b, :NG[b]] = opb * NF + otb
         odesc[b, :NG[b]] = odb
     return dict(NT=nt_max, NOT=not_max, NF=NF, NImax=NImax, NOmax=NOmax, NGmax=NGmax, NI=NI, NG=NG, iy=iy, ipair=ipair, ipos=ipos, pcoef=pcoef,
-                oy=oy, opair=opair, opos=opos, odesc=odesc)
+                oy=oy, opair=opair, opos=opos, odesc=odesc, inreal=inreal)
 
 
 def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) -> PackedProblem:
@@ -264,7 +268,7 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
         nbig = (ey >= 6.0).sum(axis=1).astype(np.int32)
     return PackedProblem(grouped=int(bool(grouped)), NImax=it["NImax"], NOmax=it["NOmax"], NGmax=it["NGmax"],
                          NF=it["NF"], NT=it["NT"], NOT=it["NOT"], NI=it["NI"], NG=it["NG"], iy=np.ascontiguousarray(it["iy"], dtype),
-                         ipair=it["ipair"], ipos=it["ipos"], pcoef=np.ascontiguousarray(it["pcoef"], dtype),
+                         ipair=it["ipair"], ipos=it["ipos"], inreal=it["inreal"], pcoef=np.ascontiguousarray(it["pcoef"], dtype),
                          oy=np.ascontiguousarray(it["oy"], dtype), opair=it["opair"], opos=it["opos"],
                          odesc=it["odesc"],
                          B=B, N=N, K=K, D=D, Umax=Umax, dtype=dtype,

@@ -60,7 +60,7 @@ int validate(const sccoda_problem* p) {
         if (p->NT < 1 || p->NT > p->NF || p->NOT < 0) return fail(-6, "grouped layout needs 1 <= NT <= NF and NOT >= 0 (got %d, %d)", p->NT, p->NOT);
         if (p->NF < 2 || (p->NF & (p->NF - 1))) return fail(-6, "grouped layout needs NF = power of two >= 2 (got %d)", p->NF);
         if ((uint64_t)p->Umax * (p->K + 1) * p->NF > 65535ull) return fail(-6, "grouped layout needs Umax*(K+1)*NF <= 65535");
-        if (!p->NI || !p->iy || !p->ipair || !p->ipos || !p->pcoef || !p->NG || !p->oy || !p->opair || !p->opos || !p->odesc)
+        if (!p->NI || !p->iy || !p->ipair || !p->ipos || !p->inreal || !p->pcoef || !p->NG || !p->oy || !p->opair || !p->opos || !p->odesc)
             return fail(-7, "grouped problem has a NULL pair/item array");
     }
     return 0;
@@ -77,10 +77,13 @@ void fill_dims(const sccoda_problem* p, sccoda::KArgs& a) {
     a.ntot = p->ntot; a.xu = p->xu;
     a.grp = p->grp; a.rstart = p->rstart; a.U = p->U; a.ref = p->ref; a.lconst = p->lconst;
     a.grouped = p->grouped ? 1 : 0;
+    // entries of the element list the value pass wants in shared memory: all of them, or (grouped layout: the counts
+    // >= 6 are read from the items) only the tail of counts below 6
+    a.el_count = a.grouped ? a.dm.NK - p->nbig_min : a.dm.NK;
     a.NImax = a.grouped ? p->NImax : 0; a.NOmax = a.grouped ? p->NOmax : 0;
     a.NGmax = a.grouped ? p->NGmax : 0; a.NF = a.grouped ? p->NF : 0;
     a.NT = a.grouped ? p->NT : 0; a.NOT = a.grouped ? p->NOT : 0;
-    a.NI = p->NI; a.iy = p->iy; a.ipair = p->ipair; a.ipos = p->ipos; a.pcoef = p->pcoef;
+    a.NI = p->NI; a.iy = p->iy; a.ipair = p->ipair; a.ipos = p->ipos; a.inreal = p->inreal; a.pcoef = p->pcoef;
     a.NG = p->NG; a.oy = p->oy; a.opair = p->opair; a.opos = p->opos; a.odesc = p->odesc;
 }
 
@@ -294,7 +297,7 @@ int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, cons
     const size_t NP = U * (K + 1), NIm = ph->grouped ? (size_t)ph->NImax : 0, NOm = ph->grouped ? (size_t)ph->NOmax : 0,
                  NGm = ph->grouped ? (size_t)ph->NGmax : 0;
     Piece gin[] = {{ph->NI, B * 4, 0}, {ph->iy, B * SCCODA_ITEM_R * NIm * ts, 0}, {ph->ipair, B * NIm * 2, 0},
-                   {ph->ipos, B * NIm * 2, 0}, {ph->pcoef, B * NP * 6 * ts, 0}, {ph->NG, B * 4, 0},
+                   {ph->ipos, B * NIm * 2, 0}, {ph->inreal, B * NIm, 0}, {ph->pcoef, B * NP * 6 * ts, 0}, {ph->NG, B * 4, 0},
                    {ph->oy, B * NOm * ts, 0}, {ph->opair, B * NGm * 2, 0}, {ph->opos, B * NGm * 2, 0},
                    {ph->odesc, B * NGm * 4, 0}};
     size_t off = 0;
@@ -331,9 +334,10 @@ int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, cons
         sccoda_problem pd = *ph;
         if (ph->grouped) {
             pd.NI = (const int32_t*)(w + gin[0].off); pd.iy = w + gin[1].off; pd.ipair = (const uint16_t*)(w + gin[2].off);
-            pd.ipos = (const uint16_t*)(w + gin[3].off); pd.pcoef = w + gin[4].off; pd.NG = (const int32_t*)(w + gin[5].off);
-            pd.oy = w + gin[6].off; pd.opair = (const uint16_t*)(w + gin[7].off); pd.opos = (const uint16_t*)(w + gin[8].off);
-            pd.odesc = (const uint32_t*)(w + gin[9].off);
+            pd.ipos = (const uint16_t*)(w + gin[3].off); pd.inreal = (const uint8_t*)(w + gin[4].off);
+            pd.pcoef = w + gin[5].off; pd.NG = (const int32_t*)(w + gin[6].off);
+            pd.oy = w + gin[7].off; pd.opair = (const uint16_t*)(w + gin[8].off); pd.opos = (const uint16_t*)(w + gin[9].off);
+            pd.odesc = (const uint32_t*)(w + gin[10].off);
         }
         pd.ey = w + in[0].off; pd.eycst = w + in[1].off; pd.eidx = (const uint32_t*)(w + in[2].off);
         pd.colperm = (const int32_t*)(w + in[3].off); pd.nbig = (const int32_t*)(w + in[4].off);

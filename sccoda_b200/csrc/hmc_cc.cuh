@@ -394,9 +394,12 @@ __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool h
         lp += (double)acc;
     }
     {
+        // When some concentration is >= c_joint (warp-uniform flag), the elements of those pairs take the joint
+        // cancellation-free form, which also carries the -lgamma(c); otherwise the packed fast loop.
+        const bool fix = __any_sync(0xffffffffu, need_fix);
         const float4* el = sp<float4>(t.el);
         float acc = 0.0f;
-        {
+        if (!fix) {
             // counts >= 6, two per lane and iteration on packed pairs; a last unpaired one alone
             f32x2 acc2 = dup2(0.0f);
             int e = lane;
@@ -411,24 +414,20 @@ __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool h
                 const float4 v = el[e];
                 acc += lgamma_shift_big(pc[__float_as_int(v.z)], v.x, v.y);
             }
-        }
 #pragma unroll 1
-        for (int e = t.nbig + lane; e < t.NK; e += 32) {
-            const float4 v = el[e];
-            acc += lgamma_shift(pc[__float_as_int(v.z)], v.x, v.y);
-        }
-        lp += (double)acc;
-        if (__any_sync(0xffffffffu, need_fix)) {
-            // concentrations >= c_joint (rare): joint cancellation-free form, which also carries the -lgamma(c)
-            double fix = 0.0;
+            for (e = t.nbig + lane; e < t.NK; e += 32) {
+                const float4 v = el[e];
+                acc += lgamma_shift(pc[__float_as_int(v.z)], v.x, v.y);
+            }
+        } else {
 #pragma unroll 1
             for (int e = lane; e < t.NK; e += 32) {
                 const float4 v = el[e];
                 const float cc = pc[__float_as_int(v.z)];
-                if (cc >= c_joint) fix += (double)lgamma_joint(cc, v.x, v.y) - (double)lgamma_shift(cc, v.x, v.y);
+                acc += cc >= c_joint ? lgamma_joint(cc, v.x, v.y) : lgamma_shift(cc, v.x, v.y);
             }
-            lp += fix;
         }
+        lp += (double)acc;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);

@@ -25,7 +25,7 @@ size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int d
         const CcPlan cp = plan_cc(a.dm.N, a.dm.K, a.NT, a.NOT);
         return cp.data_total + (size_t)chains_per_cta * cp.chain_total;
     }
-    const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem, a.grouped ? a.NImax : 0, a.NF,
+    const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem ? a.el_count : 0, a.grouped ? a.NImax : 0, a.NF,
                                   nvec_for(kind, a.max_depth), W, ts);
     return pl.data_total + (size_t)chains_per_cta * pl.chain_total;
 }

@@ -19,12 +19,14 @@ struct KArgs {
     Dims dm;
     int B, C, Umax;
     int el_smem;  // 1: stage the element list into shared memory (fp32 build, when it fits); 0: read it from global
+    int el_count; // entries staged when el_smem: N*K, or N*K - nbig_min with the grouped layout (counts < 6 only)
     int grouped;  // 1: pair / item gradient path (grouped.cuh); 0: element path (model.cuh)
     int NImax, NOmax, NGmax, NF, NT, NOT;
     const int* NI;
     const void* iy;
     const uint16_t* ipair;
     const uint16_t* ipos;
+    const uint8_t* inreal;
     const void* pcoef;
     const int* NG;
     const void* oy;
@@ -61,7 +63,7 @@ struct KArgs {
 __host__ __device__ inline size_t rnd16(size_t bytes) { return (bytes + 15) & ~size_t(15); }
 
 struct SmemPlan {
-    size_t ntot, xu, grp, rstart, colperm, el, eyc, pcoef, iy, ipair, ipos, data_total;   // per CTA
+    size_t ntot, xu, grp, rstart, colperm, el, eyc, pcoef, iy, ipair, ipos, inreal, data_total;   // per CTA
     size_t red, cp, rowterm, G, Gu, beta, ind, gk, vec, chain_total;                  // per chain (relative)
 };
 
@@ -70,7 +72,7 @@ constexpr int kItemR = 5;
 
 // nimax > 0 selects the grouped (pair / item) layout: NP = Umax*(K+1) pair records instead of (c, psi) pairs, nf
 // result slots per pair (+ one spare) instead of the per-element G, no row terms and no column-sum scratch.
-__host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int el_smem, int nimax, int nf, int nvec,
+__host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int el_count, int nimax, int nf, int nvec,
                                               int W, size_t ts) {
     SmemPlan p;
     const size_t NK = (size_t)N * K, UK = (size_t)Umax * K, P = (size_t)D + 2 * (size_t)D * (K - 1) + K;
@@ -82,12 +84,13 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
     p.grp = o; o += rnd16((size_t)N * 4);
     p.rstart = o; o += rnd16((size_t)(Umax + 1) * 4);
     p.colperm = o; o += rnd16((size_t)K * 4);
-    p.el = o; o += el_smem ? rnd16(NK * 2 * ts) : 0;
-    p.eyc = o; o += el_smem ? rnd16(NK * ts) : 0;
+    p.el = o; o += rnd16((size_t)el_count * 2 * ts);             // el_count = 0: the element list stays in global memory
+    p.eyc = o; o += rnd16((size_t)el_count * ts);
     p.pcoef = o; o += grouped ? rnd16(NP * 6 * ts) : 0;
     p.iy = o; o += grouped ? rnd16((size_t)kItemR * nimax * ts) : 0;
     p.ipair = o; o += grouped ? rnd16((size_t)nimax * 2) : 0;
     p.ipos = o; o += grouped ? rnd16((size_t)nimax * 2) : 0;
+    p.inreal = o; o += grouped ? rnd16((size_t)nimax) : 0;
     p.data_total = o;
     o = 0;
     p.red = o; o += rnd16((size_t)2 * W * 8);

@@ -47,21 +47,26 @@ __device__ __forceinline__ void stage_dataset(const KArgs& a, int b, const SmemP
     copy_to_smem(sp<int>(dt.grp), a.grp + (size_t)b * N, N);
     copy_to_smem(sp<int>(dt.rstart), a.rstart + (size_t)b * (Umax + 1), Umax + 1);
     copy_to_smem(sp<int>(dt.colperm), a.colperm + (size_t)b * K, K);
-    if (a.el_smem) {
-        Elem<T>* el = sp<Elem<T>>(dt.el);
-        for (int e = threadIdx.x; e < NK; e += blockDim.x) {   // coalesced reads, interleaved (count, index) records
-            Elem<T> v;
-            v.y = dt.ey[e];
-            v.idx = dt.eidx[e];
-            el[e] = v;
-        }
-        copy_to_smem(sp<T>(dt.eyc), dt.eycst, NK);
-    }
     dt.nbig = a.nbig[b];
+    if (a.el_smem) {
+        // (count, index) records + host constants; with the grouped layout only the tail of counts below 6 (the value
+        // pass reads the counts >= 6 from the items)
+        Elem<T>* el = sp<Elem<T>>(dt.el);
+        T* eyc = sp<T>(dt.eyc);
+        const int e0 = a.grouped ? dt.nbig : 0;
+        for (int e = threadIdx.x; e < NK - e0; e += blockDim.x) {   // coalesced reads
+            Elem<T> v;
+            v.y = dt.ey[e0 + e];
+            v.idx = dt.eidx[e0 + e];
+            el[e] = v;
+            eyc[e] = dt.eycst[e0 + e];
+        }
+    }
     dt.U = a.U[b];
     dt.ref = a.ref[b];
     dt.lconst = a.lconst[b];
     dt.pcoef = (uint32_t)pl.pcoef; dt.iy = (uint32_t)pl.iy; dt.ipair = (uint32_t)pl.ipair; dt.ipos = (uint32_t)pl.ipos;
+    dt.inreal = (uint32_t)pl.inreal;
     dt.oy = nullptr; dt.opair = nullptr; dt.opos = nullptr; dt.odesc = nullptr;
     dt.NI = 0; dt.NG = 0; dt.NImax = a.NImax; dt.NF = a.NF; dt.tot0 = Umax * K;
     if (a.grouped) {
@@ -70,6 +75,7 @@ __device__ __forceinline__ void stage_dataset(const KArgs& a, int b, const SmemP
         copy_to_smem(sp<T>(dt.iy), static_cast<const T*>(a.iy) + (size_t)b * kItemR * a.NImax, kItemR * a.NImax);
         copy_to_smem(sp<uint16_t>(dt.ipair), a.ipair + (size_t)b * a.NImax, a.NImax);
         copy_to_smem(sp<uint16_t>(dt.ipos), a.ipos + (size_t)b * a.NImax, a.NImax);
+        copy_to_smem(sp<uint8_t>(dt.inreal), a.inreal + (size_t)b * a.NImax, a.NImax);
         dt.oy = static_cast<const T*>(a.oy) + (size_t)b * a.NOmax;
         dt.opair = a.opair + (size_t)b * a.NGmax;
         dt.opos = a.opos + (size_t)b * a.NGmax;
@@ -104,7 +110,7 @@ __device__ __forceinline__ bool prologue(const KArgs& a, int nvec, DataTile<T>& 
     g.gid = threadIdx.x / TS;
     g.tid = threadIdx.x - g.gid * TS;
     c = cblk * cpc + g.gid;
-    const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem, a.grouped ? a.NImax : 0, a.NF, nvec, W,
+    const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem ? a.el_count : 0, a.grouped ? a.NImax : 0, a.NF, nvec, W,
                                   sizeof(T));
     stage_dataset<T>(a, b, pl, dt);
     carve_chain((uint32_t)(pl.data_total + (size_t)g.gid * pl.chain_total), pl, cs, g.red);

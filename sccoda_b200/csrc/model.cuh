@@ -84,6 +84,7 @@ struct DataTile {
     uint32_t iy;           // smem T[R,NImax] counts of the items
     uint32_t ipair;        // smem uint16[NImax] pair of each item
     uint32_t ipos;         // smem uint16[NImax] result slot of each item
+    uint32_t inreal;       // smem uint8[NImax] data counts of each item (value pass)
     const T* oy;           // global [NOmax] odd counts
     const uint16_t* opair; // global [NGmax] pair / result slot / (first | count << 16) of each odd group
     const uint16_t* opos;
@@ -466,38 +467,6 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     g.sync();
 }
 
-// Correction of this thread's element terms for concentrations >= c_joint (rare: far tails / nearly multinomial
-// data): replaces the standard form by the joint cancellation-free form (special.cuh), which also carries the
-// -lgamma(c) that dm_value skipped for those concentrations.  Out of line: the common path keeps its small code.
-template <typename T, int W, class Rec>
-__device__ __noinline__ double value_joint_fixup(const Dims& dm, const DataTile<T>& dt, const Rec* cp, T c_joint,
-                                                 int tid) {
-    constexpr int TS = Group<W>::SIZE;
-    double fix = 0.0;
-    if (dt.el_smem) {
-        const Elem<T>* el = sp<Elem<T>>(dt.el);
-        const T* eyc = sp<T>(dt.eyc);
-#pragma unroll 1
-        for (int e = tid; e < dm.NK; e += TS) {
-            const Elem<T> v = el[e];
-            const T c = cp[v.idx & 0xffffu].c;
-            if (c >= c_joint) fix += (double)lgamma_joint(c, v.y, eyc[e]) - (double)lgamma_shift(c, v.y, eyc[e]);
-        }
-        return fix;
-    }
-#pragma unroll 1
-    for (int e = tid; e < dm.NK; e += TS) {
-        const uint32_t ix = dt.eidx[e];
-        const T c = cp[ix & 0xffffu].c;
-        if (c >= c_joint) {
-            const T yc = sizeof(T) == 4 ? dt.eycst[e] : T(0);
-            const T y = dt.ey[e];
-            fix += (double)lgamma_joint(c, y, yc) - (double)lgamma_shift(c, y, yc);
-        }
-    }
-    return fix;
-}
-
 // Value of the log-density at theta.  Must follow dm_grad at the same theta (uses the c_uk it left in the
 // scratch).  Terms are evaluated in T, accumulated in fp64; the two O(n ln n)-sized row terms are taken in
 // fp64.  Every thread of the group receives the result.  Rec = CPsi<T> (element path) or PairRec<T> (grouped path):
@@ -541,7 +510,7 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     // fp32: concentrations >= c_joint switch to the joint (cancellation-free) form, which already contains
     // -lgamma(c); never taken in the fp64 build
     const T c_joint = sizeof(T) == 4 ? T(SCCODA_C_JOINT) : T(SCCODA_C_JOINT_F64);
-    bool need_fix = false;   // some concentration >= c_joint (rare); made group-uniform below
+    bool need_fix = false;   // some concentration >= c_joint; made group-uniform below
     {
         T acc = T(0);
         bool bad = false;
@@ -579,8 +548,59 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
         }
     }
     // elements: lgamma(c + y) - lgamma(y); per-thread partial sums in T (<= a few dozen terms), total in fp64.
-    // Concentrations >= c_joint (rare) are patched afterwards by value_joint_fixup (out of line).
-    {
+    // When some concentration is >= c_joint (uniform flag `fix`), the elements of those pairs take the joint form
+    // lgamma(c+y) - lgamma(c) - lgamma(y) instead: summing the plain form in fp32 and correcting it afterwards would
+    // leave the rounding of partial sums of size c ln c behind.
+    const bool fix = sizeof(T) == 4 && g.any(need_fix);
+    auto term_big = [&](T c, T y, T ycst) {
+        return (fix && c >= c_joint) ? lgamma_joint(c, y, ycst) : lgamma_shift_big(c, y, ycst);
+    };
+    auto term_any = [&](T c, T y, T ycst) {
+        return (fix && c >= c_joint) ? lgamma_joint(c, y, ycst) : lgamma_shift(c, y, ycst);
+    };
+    if constexpr (Rec::has_totals) {
+        // grouped layout: counts >= 6 from the items already staged for the gradient (total pairs belong to the row
+        // terms above; the Stirling remainder of a count is evaluated on the fly), counts < 6 from the tail
+        // [nbig, N*K) of the element list
+        T acc = T(0);
+        const T* iy = sp<T>(dt.iy);
+        const uint16_t* ipair = sp<uint16_t>(dt.ipair);
+        const uint8_t* inreal = sp<uint8_t>(dt.inreal);
+        const int NIs = dt.NImax;
+#pragma unroll 1
+        for (int i = tid; i < dt.NI; i += TS) {
+            const int p = ipair[i];
+            if (p >= dt.tot0) continue;
+            const T c = cp[p].c;
+            const int nr = inreal[i];
+            if (fix && c >= c_joint) {
+#pragma unroll 1
+                for (int j = 0; j < nr; ++j) {
+                    const T y = iy[j * NIs + i];
+                    acc += lgamma_joint(c, y, stirling_rem_of(y));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    if (j < nr) acc += lgamma_shift_big_auto(c, iy[j * NIs + i]);
+            }
+        }
+        const int ns = dm.NK - dt.nbig;
+        if (dt.el_smem) {
+            const Elem<T>* el = sp<Elem<T>>(dt.el);
+            const T* eyc = sp<T>(dt.eyc);
+#pragma unroll 1
+            for (int e = tid; e < ns; e += TS) {
+                const Elem<T> v = el[e];
+                acc += term_any(cp[v.idx & 0xffffu].c, v.y, eyc[e]);
+            }
+        } else {
+#pragma unroll 1
+            for (int e = dt.nbig + tid; e < dm.NK; e += TS)
+                acc += term_any(cp[__ldg(dt.eidx + e) & 0xffffu].c, __ldg(dt.ey + e), sizeof(T) == 4 ? __ldg(dt.eycst + e) : T(0));
+        }
+        lp += (double)acc;
+    } else {
         T acc = T(0);
         if (dt.el_smem) {
             const Elem<T>* el = sp<Elem<T>>(dt.el);
@@ -588,31 +608,28 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
 #pragma unroll 2
             for (int e = tid; e < dt.nbig; e += TS) {
                 const Elem<T> v = el[e];
-                acc += lgamma_shift_big(cp[v.idx & 0xffffu].c, v.y, eyc[e]);
+                acc += term_big(cp[v.idx & 0xffffu].c, v.y, eyc[e]);
             }
 #pragma unroll 1
             for (int e = dt.nbig + tid; e < dm.NK; e += TS) {
                 const Elem<T> v = el[e];
-                acc += lgamma_shift(cp[v.idx & 0xffffu].c, v.y, eyc[e]);   // mixed columns: branch on y
+                acc += term_any(cp[v.idx & 0xffffu].c, v.y, eyc[e]);   // mixed columns: branch on y
             }
-            lp += (double)acc;
         } else {
             // element list streamed from global memory (tiles too large for shared memory, fp64 parity build): same
-            // split into counts >= 6 and mixed columns, four independent loads in flight per thread
+            // split into counts >= 6 and mixed columns, independent loads in flight
             const T* __restrict__ ey = dt.ey;
             const T* __restrict__ eyc = dt.eycst;
             const uint32_t* __restrict__ eidx = dt.eidx;
 #pragma unroll 8
             for (int e = tid; e < dt.nbig; e += TS)
-                acc += lgamma_shift_big(cp[__ldg(eidx + e) & 0xffffu].c, __ldg(ey + e), sizeof(T) == 4 ? __ldg(eyc + e) : T(0));
+                acc += term_big(cp[__ldg(eidx + e) & 0xffffu].c, __ldg(ey + e), sizeof(T) == 4 ? __ldg(eyc + e) : T(0));
 #pragma unroll 1
             for (int e = dt.nbig + tid; e < dm.NK; e += TS)
-                acc += lgamma_shift(cp[__ldg(eidx + e) & 0xffffu].c, __ldg(ey + e), sizeof(T) == 4 ? __ldg(eyc + e) : T(0));
-            lp += (double)acc;
+                acc += term_any(cp[__ldg(eidx + e) & 0xffffu].c, __ldg(ey + e), sizeof(T) == 4 ? __ldg(eyc + e) : T(0));
         }
+        lp += (double)acc;
     }
-    // every thread owns a different slice of the elements in the fix-up: the flag must be uniform over the group
-    if (sizeof(T) == 4 && g.any(need_fix)) lp += value_joint_fixup<T, W, Rec>(dm, dt, cp, c_joint, tid);
     lp = g.sum(lp) + dt.lconst;
     // HalfCauchy support: -inf as soon as one sigma_d < 0 [TFP]; every thread scans the D values (uniform)
     for (int d = 0; d < D; ++d)

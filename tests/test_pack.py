@@ -145,6 +145,11 @@ def test_pair_item_layout_reproduces_brackets(shape):
             for c in (np.exp(rs.randn()), 1e-3, 250.0):
                 ref = _direct_bracket(vals, c)
                 assert abs(_layout_bracket(pk, 0, p, c) - ref) <= 1e-12 * max(1.0, abs(ref))
+            # the data counts of the pair's items (inreal per item, padding behind them) are its counts >= 6
+            mine = [i for i in range(pk.NI[0]) if pk.ipair[0, i] == p]
+            data = sorted(float(pk.iy[0, j, i]) for i in mine for j in range(int(pk.inreal[0, i])))
+            assert data == sorted(v for v in vals if v >= 6)
+            assert all(pk.iy[0, j, i] == 6.0 for i in mine for j in range(int(pk.inreal[0, i]), 5))
 
 
 def test_pair_item_layout_auto_mode():
