@@ -295,13 +295,20 @@ __device__ __forceinline__ void dm_grad_items(const Dims& dm, const DataTile<T>&
                 }
             }
         }
-        // d/d sigma_d: sum_k g_dk ind_dk b_offset_dk - HalfCauchy term (zero prior gradient below 0 [TFP])
+        // d/d sigma_d: sum_k g_dk ind_dk b_offset_dk - HalfCauchy term (zero prior gradient below 0 [TFP]); the
+        // (up to) four sums of this block of covariates share one reduction
+        if constexpr (sizeof(T) == 4) {
+            g.sumv(part);
+        } else {
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd)
+                if (d0 + dd < D) part[dd] = g.sum(part[dd]);
+        }
 #pragma unroll
         for (int dd = 0; dd < 4; ++dd) {
             if (d0 + dd < D) {
                 const T s = sigma[d0 + dd];
-                const T tot = g.sum(part[dd]);
-                if (tid == 0) epi(d0 + dd, tot - (s >= T(0) ? T(2) * s / (T(1) + s * s) : T(0)));
+                if (tid == 0) epi(d0 + dd, part[dd] - (s >= T(0) ? T(2) * s / (T(1) + s * s) : T(0)));
             }
         }
     }

@@ -501,8 +501,9 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
                             d1 = fma(sp, cp[i], d1);
                             d2 = fma(sp, p[i], d2);
                         }
-                        const double D1 = g.sum((double)d1), D2 = g.sum((double)d2);
-                        if (!(D1 >= 0.0 && D2 >= 0.0)) no_uturn = false;
+                        double dd[2] = {(double)d1, (double)d2};
+                        g.sumv(dd);
+                        if (!(dd[0] >= 0.0 && dd[1] >= 0.0)) no_uturn = false;
                     }
                 }
                 double energy = lqv - 0.5 * g.sum((double)kk);
@@ -549,8 +550,9 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
                 d2 = fma(r, rpm[i], d2);
             }
             if (forward) r_lp = lqv; else l_lp = lqv;
-            const double D1 = g.sum((double)d1), D2 = g.sum((double)d2);
-            cont = alive && (D1 >= 0.0) && (D2 >= 0.0);
+            double dd[2] = {(double)d1, (double)d2};
+            g.sumv(dd);
+            cont = alive && (dd[0] >= 0.0) && (dd[1] >= 0.0);
             depth += 1;
         }
         lp_cur = c_lp;

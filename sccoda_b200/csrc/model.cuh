@@ -136,6 +136,30 @@ struct Group {
         }
         return v;
     }
+    // NV sums at once with a single pair of barriers (the scratch holds 16 bytes per warp: two doubles / four floats)
+    template <typename V, int NV>
+    __device__ __forceinline__ void sumv(V (&v)[NV]) const {
+        static_assert(sizeof(V) * NV <= 16, "Group::sumv: 16 bytes of scratch per warp");
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+        if (W > 1) {
+            V* r = sp<V>(red);
+            sync();
+            if ((tid & 31) == 0)
+#pragma unroll
+                for (int j = 0; j < NV; ++j) r[(tid >> 5) * NV + j] = v[j];
+            sync();
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                V t = r[(tid & (W - 1)) * NV + j];
+#pragma unroll
+                for (int o = W >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                v[j] = t;
+            }
+        }
+    }
     // group-wide OR of a predicate
     __device__ __forceinline__ bool any(bool v) const {
         v = __any_sync(0xffffffffu, v) != 0;
