@@ -177,8 +177,8 @@ int sccoda_summarize(const sccoda_problem* prob, int32_t num_results, int32_t sk
 int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* warps_per_chain,
                        int32_t* chains_per_cta, int32_t* grid, int32_t* smem_bytes);
 
-/* Which kernel sccoda_sample would launch: 1 = generic HMC, 2 = NUTS, 3 = case/control HMC specialisation
- * (D == 1, Umax == 2 covariate groups, K <= 31, fp32, one warp per chain, grouped layout). */
+/* Which kernel sccoda_sample would launch: 1 = generic HMC, 2 = generic NUTS, 3 / 4 = the case/control HMC / NUTS
+ * specialisations (D == 1, Umax == 2 covariate groups, K <= 31, fp32, one warp per chain, grouped layout). */
 int sccoda_kernel_kind(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* kind);
 
 /* Host-buffer convenience (the end-to-end path): all pointers are HOST memory; copies in, runs on `device`,

@@ -235,8 +235,9 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
     if dtype == np.float32:
         lg = gammaln(ys)
         big = ys >= 6.0
-        stirling = (ys - 0.5) * np.log(ys) - ys + 0.5 * LOG_2PI
-        ycst = np.where(big, lg - stirling, lg)                 # r(y) for y >= 6, lgamma(y) otherwise
+        with np.errstate(divide="ignore", invalid="ignore"):    # exact zeros (pseudocount=False) are never "big"
+            stirling = (ys - 0.5) * np.log(ys) - ys + 0.5 * LOG_2PI
+            ycst = np.where(big, lg - stirling, lg)             # r(y) for y >= 6, lgamma(y) otherwise
         lconst = prior_const + logp_const + lg.sum(axis=(1, 2))
     else:
         ycst = np.zeros_like(ys)

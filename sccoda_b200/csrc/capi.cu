@@ -99,7 +99,7 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, i
     }
     const int NK = p->N * p->K;
     int W = W_req;
-    if (W == 0 && sccoda::select_kind(a, kind, p->dtype, 1) == sccoda::KIND_HMC_CC && (p->NT <= 8 || p->B * p->C >= 148 * 8)) {
+    if (W == 0 && sccoda::select_kind(a, kind, p->dtype, 1) != kind && (p->NT <= 8 || p->B * p->C >= 148 * 8)) {
         // case/control shape: the lane-per-cell-type kernel (one warp per chain) unless a few chains face very long
         // groups (more than 40 rows per group: the items of a pair are walked by one lane)
         W = 1;

@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ 
     const int b = blockIdx.x / ctas_per_ds;
     const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
     const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P;
-    const CcPlan pl = plan_cc(a.dm.N, K, a.NT, a.NOT);
+    const CcPlan pl = plan_cc(a.dm.N, K, a.NT, a.NOT, 0);
     CcTile tile;
     cc_stage(a, b, pl, tile);
     if (c >= a.C) return;
@@ -577,6 +577,227 @@ __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ 
     }
     __syncwarp();
     scatter(vec, thc);
+    __syncwarp();
+    store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3cc — NUTS for the same case/control shape: the iterative tree of nuts_kernel (kernels_impl.cuh; [TFP]
+// NoUTurnSampler.one_step as restated in SURVEY §8c: multinomial sampling, generalized U-turn, checkpoint memory, dual
+// averaging) on the lane-per-cell-type state.  The leaf being integrated (q, p, gradient, running momentum sum) lives
+// in registers; the tree's stored vectors are float4 slots per lane in shared memory (one LDS.128 / STS.128 each).
+// Same Philox streams and the same arithmetic per parameter as the generic kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ CcVec cc_ld(const float4* slot) {
+    const float4 v = *slot;
+    return CcVec{v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ void cc_st(float4* slot, const CcVec& v) { *slot = make_float4(v.a, v.b, v.i, v.s); }
+// per-lane part of a dot product over the flat parameter vector (sigma_d is replicated: lane 0 counts it)
+__device__ __forceinline__ float cc_dot(const CcVec& x, const CcVec& y, int lane) {
+    float d = fmaf(x.a, y.a, fmaf(x.b, y.b, x.i * y.i));
+    if (lane == 0) d = fmaf(x.s, y.s, d);
+    return d;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(128, 4) nuts_cc_kernel(const __grid_constant__ KArgs a) {
+    using T = float;
+    const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
+    const int cpc = blockDim.x >> 5;
+    const int ctas_per_ds = (a.C + cpc - 1) / cpc;
+    const int b = blockIdx.x / ctas_per_ds;
+    const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
+    const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P, maxd = a.max_depth;
+    const CcPlan pl = plan_cc(a.dm.N, K, a.NT, a.NOT, 11 + 2 * (maxd + 1));
+    CcTile tile;
+    cc_stage(a, b, pl, tile);
+    if (c >= a.C) return;
+    const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
+    const uint32_t pc_off = chain_off + (uint32_t)pl.pc;
+    T* const vec = sp<T>(chain_off + (uint32_t)pl.vec);
+    float4* const slots = sp<float4>(chain_off + (uint32_t)pl.slots) + lane;   // slot k of this lane: slots[32 * k]
+    enum { S_CQ = 0, S_CG, S_LQ, S_LP, S_LG, S_RQ, S_RP, S_RG, S_SQ, S_SG, S_RHO, S_CKP };
+    const int S_CKR = S_CKP + (maxd + 1);
+    const size_t chain = (size_t)b * a.C + c;
+    const RngKey key{(uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), a.chain_id0 + (uint32_t)chain};
+    const int ref = a.ref[b];
+
+    CcLane ln;
+    ln.K = K;
+    ln.has = lane < K;
+    ln.active = ln.has && lane != ref;
+    {
+        const T* xu = static_cast<const T*>(a.xu) + (size_t)b * 2;
+        ln.x0 = xu[0];
+        ln.x1 = a.U[b] > 1 ? xu[1] : T(0);
+    }
+    const int jj = lane - (lane > ref);
+    const int ix_b = 1 + jj, ix_i = 1 + K1 + jj, ix_a = 1 + 2 * K1 + lane;
+    auto gather = [&](const T* v) {
+        CcVec r;
+        r.s = v[0];
+        r.a = ln.has ? v[ix_a] : T(0);
+        r.b = ln.active ? v[ix_b] : T(0);
+        r.i = ln.active ? v[ix_i] : T(0);
+        return r;
+    };
+    auto scatter = [&](T* v, const CcVec& r) {
+        if (lane == 0) v[0] = r.s;
+        if (ln.has) v[ix_a] = r.a;
+        if (ln.active) {
+            v[ix_b] = r.b;
+            v[ix_i] = r.i;
+        }
+    };
+
+    Adapt<T> ad;
+    load_chain_state<T>(a, chain, vec, ad, lane, 32);
+    __syncwarp();
+    CcVec q = gather(vec), p = {0.f, 0.f, 0.f, 0.f}, gq = p, rho_s = p;
+    T* draws = static_cast<T*>(a.draws) + chain * (size_t)a.num_results * P;
+    T* stats = static_cast<T*>(a.stats) + chain * (size_t)a.num_results * SCCODA_NSTAT;
+
+    // t = step_begin - 1: pseudo-transition that evaluates the starting point through the same (single) call site of
+    // the gradient / value as the leaves of the trees.
+    double lp_cur = 0.0;
+#pragma unroll 1
+    for (int t = a.step_begin - 1; t < a.step_end; ++t) {
+        const bool boot = t < a.step_begin;
+        const T eps = ad.eps;
+        double e0 = 0.0;
+        if (!boot) {
+            T kin = T(0);
+            __syncwarp();
+#pragma unroll 1
+            for (int i = lane; i < P; i += 32) {
+                const T pm = rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
+                kin += pm * pm;
+                vec[i] = pm;
+            }
+            __syncwarp();
+            const CcVec pm = gather(vec), cq = cc_ld(slots + 32 * S_CQ), cg = cc_ld(slots + 32 * S_CG);
+            cc_st(slots + 32 * S_LQ, cq); cc_st(slots + 32 * S_LP, pm); cc_st(slots + 32 * S_LG, cg);
+            cc_st(slots + 32 * S_RQ, cq); cc_st(slots + 32 * S_RP, pm); cc_st(slots + 32 * S_RG, cg);
+            cc_st(slots + 32 * S_RHO, pm);
+            e0 = lp_cur - 0.5 * warp_sum_d((double)kin);
+        }
+        double l_lp = lp_cur, r_lp = lp_cur, c_lp = lp_cur, c_energy = e0, s_lp = lp_cur, s_en = e0;
+        double wsum = 0.0, accept_sum = 0.0;
+        int leapfrogs = 0, depth = 0;
+        bool is_acc = false, cont = true, not_div = true;
+        uint32_t leaf_serial = 0;
+        const int depth_limit = boot ? 1 : maxd;
+#pragma unroll 1
+        while (depth < depth_limit && cont) {
+            const bool forward = boot ? true : (rng_bit(key, (uint32_t)depth, (uint32_t)t, STREAM_NUTS_DIR) != 0u);
+            const int e_q = forward ? S_RQ : S_LQ, e_p = forward ? S_RP : S_LP, e_g = forward ? S_RG : S_LG;
+            const T se = forward ? eps : -eps;
+            double lqv = forward ? r_lp : l_lp;
+            if (!boot) {
+                q = cc_ld(slots + 32 * e_q);
+                p = cc_ld(slots + 32 * e_p);
+                gq = cc_ld(slots + 32 * e_g);
+                rho_s = CcVec{0.f, 0.f, 0.f, 0.f};
+            }
+            const unsigned n_leaves = 1u << depth;
+            double w_s = -CUDART_INF;
+            bool alive = true;
+#pragma unroll 1
+            for (unsigned leaf = 0; leaf < n_leaves && alive; ++leaf) {
+                if (!boot) {
+                    const T h = T(0.5) * se;
+                    p.a = fmaf(h, gq.a, p.a); p.b = fmaf(h, gq.b, p.b); p.i = fmaf(h, gq.i, p.i); p.s = fmaf(h, gq.s, p.s);
+                    q.a = fmaf(se, p.a, q.a); q.b = fmaf(se, p.b, q.b); q.i = fmaf(se, p.i, q.i); q.s = fmaf(se, p.s, q.s);
+                }
+                const CcGrad gr = cc_grad(tile, ln, q, lane);
+                gq = gr.g;
+                lqv = cc_value(tile, pc_off, ln.has, q.a, q.b, q.i, q.s, gr.c, K, lane);
+                if (boot) break;
+                {
+                    const T h = T(0.5) * se;
+                    p.a = fmaf(h, gq.a, p.a); p.b = fmaf(h, gq.b, p.b); p.i = fmaf(h, gq.i, p.i); p.s = fmaf(h, gq.s, p.s);
+                }
+                rho_s.a += p.a; rho_s.b += p.b; rho_s.i += p.i; rho_s.s += p.s;
+                const T kk = cc_dot(p, p, lane);
+                leapfrogs += 1;
+                const int idx_max = __popc(leaf >> 1);
+                bool no_uturn = true;
+                if ((leaf & 1u) == 0u) {
+                    cc_st(slots + 32 * (S_CKP + idx_max), p);
+                    cc_st(slots + 32 * (S_CKR + idx_max), rho_s);
+                } else {
+                    const int n_chk = __ffs(~leaf) - 1;  // trailing ones
+#pragma unroll 1
+                    for (int sidx = idx_max; sidx > idx_max - n_chk && no_uturn; --sidx) {
+                        const CcVec cp = cc_ld(slots + 32 * (S_CKP + sidx)), cr = cc_ld(slots + 32 * (S_CKR + sidx));
+                        const CcVec span = {rho_s.a - cr.a + cp.a, rho_s.b - cr.b + cp.b, rho_s.i - cr.i + cp.i, rho_s.s - cr.s + cp.s};
+                        const double D1 = warp_sum_d((double)cc_dot(span, cp, lane)), D2 = warp_sum_d((double)cc_dot(span, p, lane));
+                        if (!(D1 >= 0.0 && D2 >= 0.0)) no_uturn = false;
+                    }
+                }
+                double energy = lqv - 0.5 * warp_sum_d((double)kk);
+                if (isnan(energy)) energy = -CUDART_INF;
+                const double delta = energy - e0;
+                const bool divergent = !(-delta < 1000.0);
+                const double w_new = logaddexp_d(w_s, delta);
+                const double u = (double)rng_uniform<T>(key, leaf_serial++, (uint32_t)t, STREAM_NUTS_LEAF);
+                const double thresh = (w_new > -CUDART_INF) ? delta - w_new : CUDART_NAN;
+                if (log1p(-u) <= thresh) {
+                    cc_st(slots + 32 * S_SQ, q);
+                    cc_st(slots + 32 * S_SG, gq);
+                    s_lp = lqv; s_en = energy;
+                }
+                w_s = w_new;
+                accept_sum += exp(fmin(delta, 0.0));
+                if (divergent) not_div = false;
+                alive = (!divergent) && no_uturn;
+            }
+            if (boot) {
+                cc_st(slots + 32 * S_CQ, q);
+                cc_st(slots + 32 * S_CG, gq);
+                c_lp = lqv;
+                break;
+            }
+            const double tree_w = alive ? w_s : -CUDART_INF;
+            double thresh = tree_w - wsum;
+            if (isnan(thresh)) thresh = 0.0;
+            const double u = (double)rng_uniform<T>(key, (uint32_t)depth, (uint32_t)t, STREAM_NUTS_TOP);
+            if ((log1p(-u) <= thresh) && alive) {
+                cc_st(slots + 32 * S_CQ, cc_ld(slots + 32 * S_SQ));
+                cc_st(slots + 32 * S_CG, cc_ld(slots + 32 * S_SG));
+                c_lp = s_lp; c_energy = s_en; is_acc = true;
+            }
+            wsum = logaddexp_d(wsum, tree_w);
+            cc_st(slots + 32 * e_q, q);
+            cc_st(slots + 32 * e_p, p);
+            cc_st(slots + 32 * e_g, gq);
+            CcVec rho = cc_ld(slots + 32 * S_RHO);
+            rho.a += rho_s.a; rho.b += rho_s.b; rho.i += rho_s.i; rho.s += rho_s.s;
+            cc_st(slots + 32 * S_RHO, rho);
+            const double D1 = warp_sum_d((double)cc_dot(rho, cc_ld(slots + 32 * S_LP), lane));
+            const double D2 = warp_sum_d((double)cc_dot(rho, cc_ld(slots + 32 * S_RP), lane));
+            if (forward) r_lp = lqv; else l_lp = lqv;
+            cont = alive && (D1 >= 0.0) && (D2 >= 0.0);
+            depth += 1;
+        }
+        lp_cur = c_lp;
+        if (boot) continue;
+        const double lar = accept_sum > 0.0 ? log(accept_sum / (double)leapfrogs) : -CUDART_INF;
+        ad.dual(fmin(lar, 0.0), a.num_adapt, (T)a.target_accept);
+        const int r = t - a.num_burnin;
+        if (r >= 0 && a.store_draws) {
+            scatter(draws + (size_t)r * P, cc_ld(slots + 32 * S_CQ));
+            if (lane == 0)
+                write_stats<T>(stats + (size_t)r * SCCODA_NSTAT, lp_cur, lar, is_acc, eps, !not_div, leapfrogs, c_energy, cont);
+        }
+    }
+    __syncwarp();
+    scatter(vec, cc_ld(slots + 32 * S_CQ));
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
 }

@@ -7,7 +7,7 @@
 
 namespace sccoda {
 
-enum { KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2, KIND_HMC_CC = 3 /* case/control specialisation, hmc_cc.cuh */ };
+enum { KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2, KIND_HMC_CC = 3, KIND_NUTS_CC = 4 /* case/control specialisations, hmc_cc.cuh */ };
 
 }  // namespace sccoda
 
@@ -109,9 +109,10 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
 // Shared-memory plan of the case/control HMC kernel (hmc_cc.cuh): lane-major arrays at compile-time offsets first.
 struct CcPlan {
     size_t cf, yv, ov, rows, el, bounds, red, data_total;   // per CTA
-    size_t pc, vec, chain_total;               // per chain (relative)
+    size_t pc, vec, slots, chain_total;        // per chain (relative)
 };
-__host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT) {
+// n_slots: float4-per-lane vectors of the NUTS tree (0 for HMC)
+__host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT, int n_slots) {
     CcPlan p;
     size_t o = 0;
     p.cf = o; o += 6 * 32 * 8;                                   // f32x2[6][32] rational coefficients (group 0, group 1)
@@ -124,7 +125,8 @@ __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT) {
     p.data_total = o;
     p.pc = 0;                                                    // float[64] concentrations, slot u*32 + column
     p.vec = 256;                                                 // float[96] flat state vector
-    p.chain_total = 256 + 384;
+    p.slots = 256 + 384;                                         // float4[n_slots][32] stored vectors of the NUTS tree
+    p.chain_total = 256 + 384 + (size_t)n_slots * 512;
     return p;
 }
 
@@ -132,6 +134,7 @@ int nvec_for(int kind, int max_depth);
 // KIND_HMC -> KIND_HMC_CC when the problem has the case/control shape the specialised kernel is written for
 int select_kind(const KArgs& a, int kind, int dtype, int W);
 cudaError_t launch_hmc_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_nuts_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int dtype);
 cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const KArgs& a, cudaStream_t st);
 cudaError_t launch_kernel_f32(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);

@@ -244,14 +244,46 @@ def test_case_control_kernel_ragged_batches():
     assert pk.NT >= 6 and pk.NOT >= 2 and int(pk.U.min()) == 1 and int(pk.U.max()) == 2
 
 
-def test_fp32_statistical_parity_nuts():
+def test_case_control_nuts_kernel_follows_generic_kernel():
+    """Same Philox streams, same tree logic: the lane-per-cell-type NUTS kernel and the generic NUTS kernel build the
+    same trees for the first transitions in fp32 (later, rounding differences change a U-turn decision somewhere)."""
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    B, C, K = 2, 3, 12
+    xs, ys = zip(*[synthetic_dataset(90 + b, N=14, K=K) for b in range(B)])
+    ys = np.stack(ys)
+    ys[1, 2, 3] = 0
+    init = _init(np.random.RandomState(12), 1, K, B * C).reshape(B, C, -1) * 0.5
+    init[..., 0] = 1.0
+    prob = DeviceProblem(pack(np.stack(xs), ys, np.array([11, 4]), dtype=np.float32), chains=C)
+    outs = [prob.sample(init, prob.make_sampler(2, 10, 0, num_adapt=10, seed=6, max_tree_depth=6, warps_per_chain=1,
+                                                generic_only=g)) for g in (True, False)]
+    assert outs[0].kernel_kind == 2 and outs[1].kernel_kind == 4
+    d0, d1 = outs[0].draws.cpu().numpy(), outs[1].draws.cpu().numpy()
+    assert np.isfinite(d1).all()
+    n = 3
+    for name in ("leapfrogs_taken", "is_accepted", "reach_max_depth", "diverging"):
+        assert np.array_equal(outs[0].stat(name).cpu().numpy()[:, :, :n], outs[1].stat(name).cpu().numpy()[:, :, :n]), name
+    assert np.abs(d0[:, :, :n] - d1[:, :, :n]).max() < 5e-3
+    assert np.allclose(outs[0].stat("energy").cpu().numpy()[:, :, :n], outs[1].stat("energy").cpu().numpy()[:, :, :n], atol=5e-2)
+    # chunked resume is bit-identical
+    many = prob.sample(init, prob.make_sampler(2, 10, 0, num_adapt=10, seed=6, max_tree_depth=6, warps_per_chain=1), chunk=4)
+    assert many.launches > 1 and np.array_equal(many.draws.cpu().numpy(), d1)
+    assert np.array_equal(many.stats.cpu().numpy(), outs[1].stats.cpu().numpy(), equal_nan=True)
+
+
+@pytest.mark.parametrize("variant", ["generic", "case_control"])
+def test_fp32_statistical_parity_nuts(variant):
     from sccoda_b200.engine import DeviceProblem
     x, y, _ = haber_salm()
     C, nr, nb = 32, 400, 300
     init = _init(np.random.RandomState(8), 1, 8, C)
     d_ref, s_ref = _oracle_run(x, y, 5, init, 2, nr, nb, seed=31, chain_id0=0, max_tree_depth=8)
     prob = DeviceProblem.from_arrays(x, y, 5, chains=C, dtype=np.float32)
-    out = prob.sample(init[None], prob.make_sampler(2, nr, nb, seed=32, max_tree_depth=8))
+    cc = variant == "case_control"
+    out = prob.sample(init[None], prob.make_sampler(2, nr, nb, seed=32, max_tree_depth=8, warps_per_chain=1 if cc else 0,
+                                                    generic_only=not cc))
+    assert out.kernel_kind == (4 if cc else 2)
     d = out.draws.double().cpu().numpy()
     assert np.isfinite(d).all()
     lf, lf_r = out.stat("leapfrogs_taken").double().cpu().numpy()[0].mean(1), s_ref["leapfrogs_taken"][0].mean(1)

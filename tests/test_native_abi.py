@@ -79,9 +79,12 @@ def test_launch_plan_scales_warps_for_few_chains_and_big_models():
     kind = ctypes.c_int32()
     assert nat.lib().sccoda_kernel_kind(ctypes.byref(_problem(pk, 1)), ctypes.byref(_sampler()), ctypes.byref(kind)) == 0
     assert kind.value == 3
-    # ... but several warps per chain for NUTS, for the fp64 build and when the sampler asks for the generic kernel
+    # ... NUTS has its lane-per-cell-type kernel too ...
     rc, w, *_ = _plan(_problem(pk, 1), _sampler(method=2))
-    assert rc == 0 and w == 2
+    assert rc == 0 and w == 1
+    assert nat.lib().sccoda_kernel_kind(ctypes.byref(_problem(pk, 1)), ctypes.byref(_sampler(method=2)), ctypes.byref(kind)) == 0
+    assert kind.value == 4
+    # ... but several warps per chain when the sampler asks for the generic kernels
     rc, w, *_ = _plan(_problem(pk, 1), _sampler(generic_only=1))
     assert rc == 0 and w == 2
 
