@@ -153,7 +153,10 @@ typedef struct sccoda_sampler {
     int32_t warps_per_chain; /* 0 = choose automatically; 1,2,4,8,16 */
     int32_t store_draws;    /* 1 = write draws/stats (default); 0 = only carry (e.g. warm-up chunks) */
     int32_t chains_per_cta; /* 0 = choose automatically; otherwise chain groups per thread block (tuning knob) */
-    int32_t generic_only;   /* 1 = never dispatch to a shape-specialised kernel (the case/control HMC kernel); 0 = default */
+    int32_t generic_only;   /* 1 = never dispatch to a shape-specialised kernel (the case/control kernels); 0 = default */
+    int32_t freeze_spike_slab; /* 1 = sigma_d and ind_raw keep their initial values (zero momentum, zero gradient): with
+                                  sigma_d = 1 and ind_raw = 1 the density is SimpleModel's (sccoda/model/other_models.py:31-109,
+                                  beta = b_offset) up to a constant */
 } sccoda_sampler;
 
 /* Library / device info. */

@@ -129,6 +129,16 @@ class ModelData:
     n_total: np.ndarray    # [N]
     ref: int               # reference cell type index
     logp_const: float      # sum_n [lgamma(n_n+1) - sum_k lgamma(y_nk+1)]
+    freeze: bool = False   # SimpleModel runs: sigma_d and ind_raw keep their values (zero momentum, zero gradient)
+
+    def frozen_mask(self) -> np.ndarray:
+        """True for the parameters a SimpleModel run holds fixed (sigma_d and ind_raw)."""
+        D, DK1 = self.D, self.D * (self.K - 1)
+        mask = np.zeros(self.P, dtype=bool)
+        if self.freeze:
+            mask[:D] = True
+            mask[D + DK1:D + 2 * DK1] = True
+        return mask
 
     @property
     def N(self):
@@ -225,7 +235,10 @@ def grad(theta: np.ndarray, m: ModelData) -> np.ndarray:
         # HalfCauchy: zero prior gradient for sigma_d < 0 [TFP safe-input where]
         g_sigma = np.sum(g * ind * boff, axis=1) - np.where(sigma >= 0, 2.0 * sigma / (1.0 + sigma ** 2), 0.0)
         g_iraw = g * sigma[:, None] * boff * 50.0 * ind * (1.0 - ind) - iraw
-        return np.concatenate([g_sigma, g_boff.ravel(), g_iraw.ravel(), g_alpha])
+        out = np.concatenate([g_sigma, g_boff.ravel(), g_iraw.ravel(), g_alpha])
+        if m.freeze:
+            out[m.frozen_mask()] = 0.0
+        return out
 
 
 def logp_and_grad(theta, m):
@@ -272,6 +285,8 @@ def hmc_transition(theta, lp, g, eps, L, m, rng: ChainRNG, step):
     """[TFP] HamiltonianMonteCarlo.one_step: leapfrog with L gradient evaluations + Metropolis-Hastings."""
     P = theta.shape[0]
     p0 = rng.normals(P, step)
+    if m.freeze:
+        p0[m.frozen_mask()] = 0.0
     q = theta.copy()
     p = p0 + 0.5 * eps * g
     gq = g
@@ -318,6 +333,8 @@ def nuts_transition(theta, lp, g, eps, max_depth, m, rng: ChainRNG, step, max_en
     """
     P = theta.shape[0]
     p_init = rng.normals(P, step)
+    if m.freeze:
+        p_init[m.frozen_mask()] = 0.0
     e0 = lp - 0.5 * float(p_init @ p_init)
     # trajectory ends: (q, p, lp, g)
     left = (theta, p_init, lp, g)
@@ -459,6 +476,29 @@ def sample_chain(m: ModelData, init: np.ndarray, method: int, num_results: int, 
             st["energy"][r] = s["energy"]
             st["reach_max_depth"][r] = float(s["reach_max_depth"])
     return draws, st
+
+
+# --------------------------------------------------------------------------------------
+# SimpleModel (sccoda/model/other_models.py:31-109): Dirichlet-multinomial with Normal priors, no spike-and-slab
+# --------------------------------------------------------------------------------------
+def simple_theta(b: np.ndarray, alpha: np.ndarray) -> np.ndarray:
+    """State of the full model that realises SimpleModel: sigma_d = 1, b_offset = b, ind_raw = 1 (indicator = 1 to
+    machine precision), alpha."""
+    b = np.asarray(b, dtype=np.float64)
+    D = b.shape[0]
+    return np.concatenate([np.ones(D), b.ravel(), np.ones(b.size), np.asarray(alpha, dtype=np.float64)])
+
+
+def simple_logp_offset(D: int, K: int) -> float:
+    """logp_full(simple_theta(b, alpha)) - logp_SimpleModel(b, alpha): the priors of the frozen parameters,
+    HalfCauchy(0,1) at sigma_d = 1 (:703-707 of scCODA_model.py) and Normal(0,1) at ind_raw = 1 (:717-722)."""
+    return D * (LOG_2_OVER_PI - math.log(2.0)) + D * (K - 1) * (-0.5 - 0.5 * LOG_2PI)
+
+
+def simple_logp(b: np.ndarray, alpha: np.ndarray, m: ModelData) -> float:
+    """SimpleModel.target_log_prob_fn (other_models.py:70-104): b ~ N(0,1), alpha ~ N(0,5), beta = b with a zero
+    reference column, y ~ DirichletMultinomial(exp(alpha + x beta))."""
+    return logp(simple_theta(b, alpha), m) - simple_logp_offset(m.D, m.K)
 
 
 # --------------------------------------------------------------------------------------

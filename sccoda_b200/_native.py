@@ -59,7 +59,7 @@ class Sampler(ctypes.Structure):
                 ("step_size", ctypes.c_double), ("target_accept", ctypes.c_double),
                 ("seed", ctypes.c_uint64), ("chain_id0", ctypes.c_uint32), ("warps_per_chain", ctypes.c_int32),
                 ("store_draws", ctypes.c_int32), ("chains_per_cta", ctypes.c_int32),
-                ("generic_only", ctypes.c_int32)]
+                ("generic_only", ctypes.c_int32), ("freeze_spike_slab", ctypes.c_int32)]
 
 
 _lib = None

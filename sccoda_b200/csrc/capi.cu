@@ -150,6 +150,7 @@ int fill_sampler(const sccoda_sampler* s, sccoda::KArgs& a, int* kind) {
         return fail(-16, "bad step range [%d,%d)", a.step_begin, a.step_end);
     a.store_draws = s->store_draws;
     a.generic_only = s->generic_only ? 1 : 0;
+    a.dm.freeze = s->freeze_spike_slab ? 1 : 0;
     a.step_size = s->step_size; a.target_accept = s->target_accept; a.seed = s->seed; a.chain_id0 = s->chain_id0;
     *kind = s->method == SCCODA_METHOD_NUTS ? sccoda::KIND_NUTS : sccoda::KIND_HMC;
     return 0;

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ 
             __syncwarp();
 #pragma unroll 1
             for (int i = lane; i < P; i += 32) {
-                const T p = rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
+                const T p = frozen_param(a.dm, i) ? T(0) : rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
                 kin += p * p;
                 vec[i] = p;
             }
@@ -528,6 +528,7 @@ __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ 
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
             gr = cc_grad(tile, ln, q, lane);
+            if (a.dm.freeze) gr.g.s = gr.g.i = T(0);   // SimpleModel: sigma_d and ind_raw stay where they are
             if (!boot) {
                 const bool last = (l == nl - 1);
                 const T f = last ? T(0.5) * eps : eps;
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(128, 4) nuts_cc_kernel(const __grid_constant__
             __syncwarp();
 #pragma unroll 1
             for (int i = lane; i < P; i += 32) {
-                const T pm = rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
+                const T pm = frozen_param(a.dm, i) ? T(0) : rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
                 kin += pm * pm;
                 vec[i] = pm;
             }
@@ -716,6 +717,7 @@ __global__ void __launch_bounds__(128, 4) nuts_cc_kernel(const __grid_constant__
                 }
                 const CcGrad gr = cc_grad(tile, ln, q, lane);
                 gq = gr.g;
+                if (a.dm.freeze) gq.s = gq.i = T(0);
                 lqv = cc_value(tile, pc_off, ln.has, q.a, q.b, q.i, q.s, gr.c, K, lane);
                 if (boot) break;
                 {

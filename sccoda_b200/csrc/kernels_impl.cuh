@@ -128,11 +128,20 @@ __device__ __forceinline__ bool prologue(const KArgs& a, int nvec, DataTile<T>& 
 #define SCCODA_BOUNDS(W) __launch_bounds__((W) <= 4 ? 128 : 32 * (W), (W) <= 4 ? 7 : 1)
 
 // Gradient / value of the path the kernel was instantiated for (GR: grouped pair/item layout).
+// hands a zero gradient to the epilogue for the frozen parameters of a SimpleModel run (Dims::freeze)
+template <typename T, class Epi>
+struct FrozenEpi {
+    const Epi& epi;
+    const Dims& dm;
+    __device__ __forceinline__ void operator()(int i, T gr) const { epi(i, frozen_param(dm, i) ? T(0) : gr); }
+};
+
 template <typename T, int W, bool GR, class Epi>
 __device__ __forceinline__ void grad_of(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs, uint32_t theta_off,
                                         const Group<W>& g, const Epi& epi) {
-    if constexpr (GR) dm_grad_items<T, W>(dm, dt, cs, theta_off, g, epi);
-    else dm_grad<T, W>(dm, dt, cs, theta_off, g, epi);
+    const FrozenEpi<T, Epi> fe{epi, dm};
+    if constexpr (GR) dm_grad_items<T, W>(dm, dt, cs, theta_off, g, fe);
+    else dm_grad<T, W>(dm, dt, cs, theta_off, g, fe);
 }
 template <typename T, int W, bool GR>
 __device__ __forceinline__ double value_of(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
@@ -305,7 +314,7 @@ __global__ void SCCODA_BOUNDS(W) hmc_kernel(const __grid_constant__ KArgs a) {
             T* qa = sp<T>(o_a);
 #pragma unroll 1
             for (int i = tid; i < P; i += TS) {
-                const T p = rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
+                const T p = frozen_param(a.dm, i) ? T(0) : rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
                 kin += p * p;
                 const T m = fma(T(0.5) * eps, gc[i], p);
                 mom[i] = m;
@@ -429,7 +438,7 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
             T kin = T(0);
 #pragma unroll 1
             for (int i = tid; i < P; i += TS) {
-                const T pm = rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
+                const T pm = frozen_param(a.dm, i) ? T(0) : rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
                 kin += pm * pm;
                 lq[i] = cq[i]; lpm[i] = pm; lg[i] = cg[i];
                 rq[i] = cq[i]; rpm[i] = pm; rg[i] = cg[i];

@@ -42,7 +42,13 @@ struct Dims {
     int DK1;   // D*(K-1)
     int NK;    // N*K
     uint32_t magicK, magicK1;  // ceil(2^32/K), ceil(2^32/(K-1)); 0 encodes a divisor of 1
+    int freeze;                // 1: sigma_d and ind_raw are frozen (zero momentum, zero gradient): SimpleModel
 };
+
+// is parameter i one of the frozen ones (sigma_d, ind_raw) of a run with Dims::freeze?
+__device__ __forceinline__ bool frozen_param(const Dims& dm, int i) {
+    return dm.freeze && (i < dm.D || (i >= dm.D + dm.DK1 && i < dm.D + 2 * dm.DK1));
+}
 
 __device__ __forceinline__ int fast_div(int e, uint32_t magic) {
     return magic ? (int)__umulhi((uint32_t)e, magic) : e;

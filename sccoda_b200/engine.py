@@ -92,14 +92,15 @@ class DeviceProblem:
     def make_sampler(self, method: int, num_results: int, num_burnin: int, num_adapt: Optional[int] = None,
                      num_leapfrog: int = 10, max_tree_depth: int = 10, step_size: float = 0.01,
                      target_accept: float = 0.75, seed: int = 0, chain_id0: int = 0,
-                     warps_per_chain: int = 0, chains_per_cta: int = 0, generic_only: bool = False) -> nat.Sampler:
+                     warps_per_chain: int = 0, chains_per_cta: int = 0, generic_only: bool = False,
+                     freeze_spike_slab: bool = False) -> nat.Sampler:
         if num_adapt is None:
             num_adapt = int(0.8 * num_burnin)            # scCODA_model.py:284-285
         return nat.Sampler(method=method, num_results=num_results, num_burnin=num_burnin, num_adapt=num_adapt,
                            num_leapfrog=num_leapfrog, max_tree_depth=max_tree_depth, step_begin=0, step_end=0,
                            step_size=step_size, target_accept=target_accept, seed=seed, chain_id0=chain_id0,
                            warps_per_chain=warps_per_chain, store_draws=1, chains_per_cta=chains_per_cta,
-                           generic_only=int(bool(generic_only)))
+                           generic_only=int(bool(generic_only)), freeze_spike_slab=int(bool(freeze_spike_slab)))
 
     def plan(self, smp: nat.Sampler):
         w, c, g, s = (ctypes.c_int32() for _ in range(4))

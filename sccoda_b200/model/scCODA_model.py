@@ -106,7 +106,7 @@ class CompositionalModel:
         smp = prob.make_sampler(method, int(num_results), int(num_burnin), kernel.get("num_adapt_steps"),
                                 int(kernel.get("num_leapfrog_steps", 10)), int(kernel.get("max_tree_depth", 10)),
                                 float(kernel.get("step_size", 0.01)), float(kernel.get("target_accept_prob", 0.75)),
-                                seed=int(seed))
+                                seed=int(seed), freeze_spike_slab=bool(kernel.get("freeze_spike_slab", False)))
         total = num_burnin + num_results
         verbose = bool(kernel.get("verbose", False))
         progress, chunk = None, None
