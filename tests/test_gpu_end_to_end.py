@@ -184,3 +184,18 @@ def test_sweep_hdis_on_device_match_host_summary_logic():
             lo, hi = o.hdi(eff[:, j], 0.94)
             assert np.allclose(e_hdi[b, k], [lo, hi], atol=2e-5, equal_nan=True), (b, k, e_hdi[b, k], lo, hi)
             j += 1
+
+
+def test_reference_sweep_in_one_launch(data_salm):
+    """BASELINE config 4 through the API: the 8 refits of the tutorial's reference sweep as one batch.  The tutorial
+    (Modeling_options_and_result_analysis.ipynb:880-915) finds Enterocyte credible under 7 of 8 references (it is the
+    reference itself in the eighth) and nothing else."""
+    from sccoda_b200.util.comp_ana import reference_sweep
+    times, res = reference_sweep(data_salm, "Condition", num_results=6000, num_burnin=2000, num_chains=4, seed=1)
+    assert times.shape == (1, 8) and len(res["references"]) == 8
+    row = times.iloc[0]
+    assert row["Enterocyte"] >= 6
+    assert (row.drop("Enterocyte") <= 1).all()
+    assert res["inclusion_prob"].shape == (8, 8)
+    for r in range(8):
+        assert res["inclusion_prob"][r, r] == 0.0            # the reference column has no effect

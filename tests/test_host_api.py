@@ -201,3 +201,15 @@ def test_inclusion_threshold_matches_oracle_restatement():
         beta = rs.randn(S, D, K) * (rs.rand(S, D, K) < rs.rand(1, D, K))
         inc, nz, thr, final = o.inclusion_and_effects(beta, 0.1)
         assert res.inclusion_threshold(inc, 0.1) == thr
+
+
+def test_automatic_reference_batch_matches_per_dataset_rule():
+    from sccoda_b200.util.comp_ana import automatic_reference, automatic_reference_batch
+    from sccoda_b200.util.data_generation import generate_sweep
+    _, y, _ = generate_sweep(24, K=9, n_per_group=6, n_total=400)
+    y[3, :, 2] = 0                                   # a cell type that is absent everywhere cannot be the reference
+    refs = automatic_reference_batch(y, 0.2)
+    assert refs.shape == (24,) and refs[3] != 2
+    assert [int(r) for r in refs] == [automatic_reference(y[b], 0.2) for b in range(24)]
+    with pytest.raises(ValueError, match="large enough presence"):
+        automatic_reference_batch(np.zeros((2, 4, 3)))
