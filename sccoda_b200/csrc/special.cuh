@@ -127,7 +127,7 @@ __device__ __forceinline__ float lgamma_shift(float c, float y, float ycst) {
 // so that the O(c ln c) parts of lgamma(c+y) and lgamma(c) never appear (fp32 would lose them):
 //   y >= 6: (c-1/2) log1p(y/c) + (y-1/2) log1p(c/y) + ln(z)/2 - ln(2 pi)/2 + r(z) - r(c) - r(y)   [ycst = r(y)]
 //   y <  6: (c-1/2) log1p(y/c) + y (ln z - 1) + r(z) - r(c) - lgamma(y)                           [ycst = lgamma(y)]
-#define SCCODA_C_JOINT 64.0f
+#define SCCODA_C_JOINT 256.0f
 __device__ __forceinline__ float lgamma_joint(float c, float y, float ycst) {
     const float z = c + y;
     const float rc = rcp_fast(c);
