@@ -338,11 +338,13 @@ def run_ours(a):
     achieved_tf = flops_launch / (k_ms * 1e-3) / 1e12
     peaks, peak_kind = measured_peaks()
     draw_bytes = float(B) * C * a.num_results * (P + nat.NSTAT) * 4
+    traffic = traffic_from_profile(out.kernel_kind, a)
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None, "traffic": traffic_from_profile(out.kernel_kind, a),
+                "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None,
+                "traffic": traffic["bytes"] if traffic else None, "traffic_detail": traffic,
                 "peak_source": "FFMA micro-kernel measured in this run on this device (sccoda_measure_peaks); "
                                "MEASURED_PEAKS.json has no fp32 entry",
-                "mufu_peak_tops": mufu_peak, "kernel": {1: "hmc_kernel<float,W,grouped>", 3: "hmc_cc_kernel"}.get(out.kernel_kind, "hmc_kernel"), "kernel_ms": k_ms,
+                "mufu_peak_tops": mufu_peak, "kernel": {1: "hmc_kernel<float,W,grouped>", 3: "hmc_cc_kernel", 5: "hmc_mg_kernel<D>"}.get(out.kernel_kind, "hmc_kernel"), "kernel_ms": k_ms,
                 "algorithmic_flop_per_launch": flops_launch,
                 "flop_model": "per grad-eval 64NK+48N+4NKD, per value 28(2NK+2N) (SURVEY 8d)",
                 "hbm": {"achieved_gbs": draw_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),

@@ -356,7 +356,7 @@ __device__ __forceinline__ CcGrad cc_grad(const CcTile& t, const CcLane& ln, con
 // ------------------------------------------------------------------------------------------------
 // Value of the log-density (same terms, guards and precision strategy as dm_value in model.cuh)
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool has, float qa, float qb, float qi, float qs,
+static __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool has, float qa, float qb, float qi, float qs,
                                         f32x2 c, int K, int lane) {
     float* pc = sp<float>(pc_off);
     const float c0 = lo2(c), c1 = hi2(c);
@@ -436,6 +436,7 @@ __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off, bool h
     return lp;
 }
 
+#ifndef SCCODA_CC_HELPERS_ONLY   // hmc_mg.cuh reuses the helpers above, not the kernels
 // ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
@@ -803,5 +804,7 @@ __global__ void __launch_bounds__(128, 4) nuts_cc_kernel(const __grid_constant__
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
 }
+
+#endif  // SCCODA_CC_HELPERS_ONLY
 
 }  // namespace sccoda

@@ -1,0 +1,508 @@
+// K2mg — HMC on the lane-per-cell-type layout of hmc_cc.cuh for designs with MORE than two covariate groups:
+// up to 8 groups (distinct rows of the design matrix: four conditions, a 2x2 or 2x2x2 factorial ...), D <= 3
+// covariates, K <= 31 cell types, fp32, one warp per chain.
+//
+// Same algorithm, Philox streams and per-parameter arithmetic as hmc_kernel (kernels_impl.cuh; reference:
+// sccoda/model/scCODA_model.py:276-315, :382-424) and the same pair / item formulation of the gradient as
+// hmc_cc_kernel.  Lane k owns cell type k (lane K the row totals): alpha_k and, per covariate d, b_offset_dk,
+// ind_raw_dk with their momenta and gradients are registers; sigma_d is replicated.  The covariate groups are
+// walked two at a time on packed fp32 pairs (FFMA2); group pair `up` covers groups 2 up and 2 up + 1, an odd
+// group count leaves the last slot empty (no rows, no items, zero coefficients -> contributes nothing).
+// The case/control kernel stays the special case D == 1, two groups (everything of a lane fits 72 registers there).
+#pragma once
+#define SCCODA_CC_HELPERS_ONLY
+#include "hmc_cc.cuh"
+
+namespace sccoda {
+
+struct MgTile {
+    uint32_t cf, yv, ov, rows, el, xg, cnt, bnd;   // shared-memory byte offsets (MgPlan)
+    uint32_t yv_stride, ov_stride;                 // bytes per pair of groups
+    int UP, UPmax;                                 // pairs of groups of THIS dataset / of the fullest dataset of the batch
+    int N, NK, nbig;
+    double lconst;
+};
+
+// (group u, column) of pair index p = u*K + k (cell types) or Umax*K + u (row totals -> column K)
+__device__ __forceinline__ void mg_pair_to_col(int p, int K, int Umax, int& u, int& col) {
+    if (p >= Umax * K) {
+        u = p - Umax * K;
+        col = K;
+    } else {
+        u = p / K;
+        col = p - u * K;
+    }
+}
+
+// keeps a shared-memory offset in a register: without it the compiler rebuilds the offsets from the launch
+// arguments (a few dozen integer instructions) wherever register pressure is high
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
+}
+
+// Staging: the packed dataset (include/sccoda_b200.h) re-laid lane-major, one block per pair of groups
+__device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl, int UPmax, MgTile& t) {
+    using T = float;
+    const int N = a.dm.N, K = a.dm.K, D = a.dm.D, NK = a.dm.NK, Umax = a.Umax, NP = Umax * (K + 1);
+    const int NT = a.NT, NOT = a.NOT;
+    t.cf = pin_u32((uint32_t)pl.cf); t.yv = pin_u32((uint32_t)pl.yv); t.ov = pin_u32((uint32_t)pl.ov);
+    t.rows = pin_u32((uint32_t)pl.rows); t.el = pin_u32((uint32_t)pl.el); t.xg = pin_u32((uint32_t)pl.xg);
+    t.cnt = pin_u32((uint32_t)pl.cnt); t.bnd = pin_u32((uint32_t)pl.bounds);
+    t.yv_stride = pin_u32((uint32_t)(NT * kItemR * 32 * 8)); t.ov_stride = pin_u32((uint32_t)(NOT * 32 * 8));
+    t.N = N; t.NK = NK;
+    t.UP = (a.U[b] + 1) >> 1;
+    t.UPmax = UPmax;
+    // [up]: items, [UPmax + up]: odd counts of the fullest pair of the group pair, [2 UPmax]: elements with a count >= 6
+    int* bounds = sp<int>((uint32_t)pl.bounds);
+    if (threadIdx.x < 2 * UPmax + 1) bounds[threadIdx.x] = 0;
+    const int* rstart = a.rstart + (size_t)b * (Umax + 1);
+    float* cnt = sp<float>((uint32_t)pl.cnt);
+    if (threadIdx.x < 2 * UPmax) {
+        const int u = threadIdx.x;
+        cnt[u] = u < Umax ? (float)(rstart[u + 1] - rstart[u]) : 0.0f;
+    }
+    // covariate values of the groups: xg[up][d] = (x of group 2 up, x of group 2 up + 1)
+    float* xg = sp<float>((uint32_t)pl.xg);
+    const T* xu = static_cast<const T*>(a.xu) + (size_t)b * Umax * D;
+    for (int i = threadIdx.x; i < UPmax * D * 2; i += blockDim.x) {
+        const int h = i & 1, r = i >> 1, up = r / D, d = r - up * D, u = 2 * up + h;
+        xg[i] = u < Umax ? xu[u * D + d] : 0.0f;
+    }
+    float* cf = sp<float>((uint32_t)pl.cf);
+    float* yv = sp<float>((uint32_t)pl.yv);
+    float* ov = sp<float>((uint32_t)pl.ov);
+    const T* pcoef = static_cast<const T*>(a.pcoef) + (size_t)b * NP * 6;
+    // rational coefficients: cf[up][j][lane] = (pair (2 up, lane), pair (2 up + 1, lane)); lane K = row totals
+    for (int i = threadIdx.x; i < UPmax * 6 * 32 * 2; i += blockDim.x) {
+        const int h = i & 1, lane = (i >> 1) & 31, r = i >> 6, up = r / 6, j = r - up * 6, u = 2 * up + h;
+        float v = 0.0f;
+        if (lane <= K && u < Umax) v = pcoef[(lane < K ? u * K + lane : Umax * K + u) * 6 + j];
+        cf[i] = v;
+    }
+    // item and odd counts: padding is the count 6, which contributes psi(c+6) - psi(c+6) = 0
+    for (int i = threadIdx.x; i < UPmax * NT * kItemR * 64; i += blockDim.x) yv[i] = 6.0f;
+    for (int i = threadIdx.x; i < UPmax * NOT * 64; i += blockDim.x) ov[i] = 6.0f;
+    __syncthreads();
+    const T* iy = static_cast<const T*>(a.iy) + (size_t)b * kItemR * a.NImax;
+    const uint16_t* ipair = a.ipair + (size_t)b * a.NImax;
+    const uint16_t* ipos = a.ipos + (size_t)b * a.NImax;
+    const int NI = a.NI[b];
+    for (int i = threadIdx.x; i < NI * kItemR; i += blockDim.x) {
+        const int j = i / NI, it = i - j * NI;
+        const int p = ipair[it], tt = ipos[it] - p * a.NF;
+        int u, col;
+        mg_pair_to_col(p, K, Umax, u, col);
+        const int up = u >> 1;
+        yv[(((up * NT + tt) * kItemR + j) * 32 + col) * 2 + (u & 1)] = iy[j * a.NImax + it];
+        if (j == 0) atomicMax(&bounds[up], tt + 1);
+    }
+    const int NG = a.NG[b];
+    const T* oy = static_cast<const T*>(a.oy) + (size_t)b * a.NOmax;
+    for (int q = threadIdx.x; q < NG; q += blockDim.x) {
+        const uint32_t od = a.odesc[(size_t)b * a.NGmax + q];
+        int u, col;
+        mg_pair_to_col(a.opair[(size_t)b * a.NGmax + q], K, Umax, u, col);
+        const int up = u >> 1;
+        for (int tt = 0; tt < (int)(od >> 16); ++tt) ov[((up * NOT + tt) * 32 + col) * 2 + (u & 1)] = oy[(od & 0xffffu) + tt];
+        atomicMax(&bounds[UPmax + up], (int)(od >> 16));
+    }
+    // value pass, rows and elements: as in cc_stage (hmc_cc.cuh), concentration slot = group * 32 + column
+    float4* rows = sp<float4>((uint32_t)pl.rows);
+    const T* ntot = static_cast<const T*>(a.ntot) + (size_t)b * N;
+    const int* grp = a.grp + (size_t)b * N;
+    double lg_sum = 0.0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const double nn = (double)ntot[n];
+        const double lg = lgamma(nn);
+        const double rc = nn >= 6.0 ? lg - ((nn - 0.5) * log(nn) - nn + 0.91893853320467274178) : lg;
+        rows[n] = make_float4((float)nn, (float)rc, __int_as_float(grp[n] * 32 + K), 0.0f);
+        lg_sum += lg;
+    }
+    double* red = sp<double>((uint32_t)pl.red);
+    if (threadIdx.x < 4) red[threadIdx.x] = 0.0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) lg_sum += __shfl_xor_sync(0xffffffffu, lg_sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lg_sum;   // one slot per warp: deterministic sum below
+    float4* el = sp<float4>((uint32_t)pl.el);
+    const T* ey = static_cast<const T*>(a.ey) + (size_t)b * NK;
+    const T* eycst = static_cast<const T*>(a.eycst) + (size_t)b * NK;
+    const uint32_t* eidx = a.eidx + (size_t)b * NK;
+    if (threadIdx.x < 32) {
+        // counts >= 6 first; partitioned by warp 0 with ballots, in list order (launch-independent summation order)
+        const int lane = threadIdx.x;
+        int nbig = 0;
+        for (int base = 0; base < NK; base += 32) nbig += __popc(__ballot_sync(0xffffffffu, base + lane < NK && ey[base + lane] >= 6.0f));
+        int ib = 0, is = nbig;
+        for (int base = 0; base < NK; base += 32) {
+            const int e = base + lane;
+            const bool in = e < NK;
+            const float y = in ? ey[e] : 0.0f;
+            const bool big = in && y >= 6.0f;
+            const uint32_t mb = __ballot_sync(0xffffffffu, big), ms = __ballot_sync(0xffffffffu, in && !big);
+            const uint32_t lt = (1u << lane) - 1u;
+            if (in) {
+                const int uk = (int)(eidx[e] & 0xffffu);
+                const int u = uk / K;
+                const int dst = big ? ib + __popc(mb & lt) : is + __popc(ms & lt);
+                el[dst] = make_float4(y, eycst[e], __int_as_float(u * 32 + (uk - u * K)), 1.0f / y);
+            }
+            ib += __popc(mb);
+            is += __popc(ms);
+        }
+        if (lane == 0) bounds[2 * UPmax] = nbig;
+    }
+    __syncthreads();
+    t.nbig = bounds[2 * UPmax];
+    t.lconst = a.lconst[b] - (((red[0] + red[1]) + red[2]) + red[3]);
+}
+
+// The parameters a lane owns: alpha_k and, per covariate, b_offset_dk, ind_raw_dk (zero on the reference lane and on
+// lanes >= K) and sigma_d (uniform).
+template <int D>
+struct MgVec {
+    float a, b[D], i[D], s[D];
+};
+template <int D>
+__device__ __forceinline__ MgVec<D> mg_zero() {
+    MgVec<D> v;
+    v.a = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) v.b[d] = v.i[d] = v.s[d] = 0.0f;
+    return v;
+}
+// y = f x + y
+template <int D>
+__device__ __forceinline__ void mg_axpy(MgVec<D>& y, float f, const MgVec<D>& x) {
+    y.a = fmaf(f, x.a, y.a);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        y.b[d] = fmaf(f, x.b[d], y.b[d]);
+        y.i[d] = fmaf(f, x.i[d], y.i[d]);
+        y.s[d] = fmaf(f, x.s[d], y.s[d]);
+    }
+}
+
+struct MgLane {
+    int K;
+    bool has, active;    // lane < K; lane < K and lane != ref
+};
+
+// Gradient of the log-density at q, pair / item formulation; the concentrations of every group are left
+// in the chain's shared-memory slots pc[group * 32 + column] (column K: S_u) for the value pass.
+template <int D>
+__device__ __forceinline__ MgVec<D> mg_grad(const MgTile& t, const MgLane& ln, const MgVec<D>& q, uint32_t pc_off, int lane) {
+    float id[D], bet[D], tg[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        id[d] = ln.active ? sigmoid_stable(50.0f * q.i[d]) : 0.0f;            // (:724-734)
+        bet[d] = id[d] * q.s[d] * q.b[d];
+        tg[d] = 0.0f;
+    }
+    float ga = 0.0f;
+    uint32_t cf_off = t.cf + lane * 8, yv_off = t.yv + lane * 8, ov_off = t.ov + lane * 8, xg_off = t.xg;
+    uint32_t pcw = pc_off + lane * 4;
+    const float* cnt = sp<float>(t.cnt);
+    const int* bnd = sp<int>(t.bnd);
+    __syncwarp();
+#pragma unroll 1
+    for (int up = 0; up < t.UP; ++up) {
+        const f32x2* xg = sp<f32x2>(xg_off);
+        f32x2 lin = dup2(q.a);
+#pragma unroll
+        for (int d = 0; d < D; ++d) lin = fma2(xg[d], dup2(bet[d]), lin);
+        f32x2 c = exp2_acc(lin);                                                  // (:743)
+        if (cnt[2 * up + 1] == 0.0f) c = pk2(lo2(c), 1.0f);                       // empty slot of an odd group count
+        const float c0 = ln.has ? lo2(c) : 0.0f, c1 = ln.has ? hi2(c) : 0.0f;
+        const float S = warp_sum2(c0, c1, lane);                                  // lanes 0..15: S_0, lanes 16..31: S_1
+        const float So = __shfl_xor_sync(0xffffffffu, S, 16);
+        if (lane == ln.K) c = lane < 16 ? pk2(S, So) : pk2(So, S);
+        *sp<float>(pcw) = lo2(c);
+        *sp<float>(pcw + 128) = hi2(c);
+        // reference point of the items: x6 = c + 5.5, w6 = 1/x6, a = w6^5, nb = -5 (psi(c+6) - ln x6)
+        const f32x2 cm = add2(c, dup2(-0.5f));
+        const f32x2 w6 = rcp2(add2(c, dup2(5.5f)));
+        const f32x2 w62 = mul2(w6, w6);
+        const f32x2 a5 = mul2(mul2(w62, w62), w6);
+        const f32x2 nb = mul2(psi_mid_acc2(w6, dup2(0.0f)), dup2(-(float)SCCODA_ITEM_R));
+        // brackets Br = rational sum_i W_i/(c+i) + items + odd counts, both groups at once
+        f32x2 br = pair_rational2(c, sp<f32x2>(cf_off));
+        const f32x2* yv = sp<f32x2>(yv_off);
+        const int nt = bnd[up], n_odd = bnd[t.UPmax + up];
+#pragma unroll 1
+        for (int tt = 0; tt < nt; ++tt, yv += SCCODA_ITEM_R * 32) br = add2(br, item_eval2(cm, a5, nb, yv));
+        if (n_odd > 0) {
+            // counts below 6 that are not in {0..5} (the 0.5 pseudocount, non-integer data), one by one
+            const f32x2 x6 = add2(c, dup2(5.5f));
+            const f32x2 nref = fma2(lg2_2(x6), dup2(-SCCODA_LN2F), mul2(nb, dup2(1.0f / (float)SCCODA_ITEM_R)));   // -psi(c+6)
+            yv = sp<f32x2>(ov_off);
+#pragma unroll 1
+            for (int tt = 0; tt < n_odd; ++tt, yv += 32) br = add2(br, add2(psi_any2(add2(c, *yv)), nref));
+        }
+        // d logp / d log c_uk = c_uk (Br_uk - Br_total(u)), chain rule through alpha and the effects
+        const float bt0 = __shfl_sync(0xffffffffu, lo2(br), ln.K), bt1 = __shfl_sync(0xffffffffu, hi2(br), ln.K);
+        const float G0 = c0 * (lo2(br) - bt0), G1 = c1 * (hi2(br) - bt1);        // c0 = c1 = 0 on lanes >= K
+        ga += G0 + G1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const f32x2 xv = xg[d];
+            tg[d] = fmaf(lo2(xv), G0, fmaf(hi2(xv), G1, tg[d]));
+        }
+        cf_off += 6 * 32 * 8; yv_off += t.yv_stride; ov_off += t.ov_stride; xg_off += D * 8; pcw += 256;
+    }
+    MgVec<D> g;
+    g.a = fmaf(q.a, -0.04f, ga);                                               // d/d alpha_k
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const float tgi = tg[d] * id[d];                                       // id == 0 on inactive lanes
+        g.b[d] = fmaf(tgi, q.s[d], -q.b[d]);                                   // d/d b_offset_dk
+        g.i[d] = fmaf(tgi * q.s[d] * q.b[d], 50.0f * (1.0f - id[d]), -q.i[d]); // d/d ind_raw_dk
+        // d/d sigma_d: sum_k g_k ind_k b_offset_k - HalfCauchy term (zero prior gradient below 0 [TFP])
+        g.s[d] = warp_sum1(tgi * q.b[d]) - (q.s[d] >= 0.0f ? 2.0f * q.s[d] * rcp_fast(fmaf(q.s[d], q.s[d], 1.0f)) : 0.0f);
+    }
+    return g;
+}
+
+// Value of the log-density from the concentrations the last gradient evaluation left in pc (same terms, guards and
+// precision strategy as cc_value / dm_value); `prior` is the lane's share of the parameter priors.
+static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off, bool has, float prior, bool neg_sigma, int K, int lane) {
+    const float* pc = sp<float>(pc_off);
+    __syncwarp();
+    double lp = (double)prior;
+    // DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c)                               (:746-751)
+    // Guard (numerics): beyond c_max the lgamma differences have lost all precision => NaN => rejected.
+    const float c_max = 1e6f, c_joint = SCCODA_C_JOINT;
+    bool need_fix = false, bad = false;
+    if (has) {
+        const float* cnt = sp<float>(t.cnt);
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int u = 0; u < 2 * t.UP; ++u) {
+            const float cu = pc[u * 32 + lane];
+            if (cu < c_joint) acc = fmaf(-cnt[u], lgamma_pos(cu), acc); else need_fix = true;
+            bad = bad || !(cu <= c_max);
+        }
+        lp += (double)acc;
+    }
+    if (bad) lp = CUDART_NAN;
+    {
+        // rows: -[lgamma(S_u + n) - lgamma(S_u) - lgamma(n)], joint form for S_u >= 6 (the usual case)
+        const float4* rows = sp<float4>(t.rows);
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int n = lane; n < t.N; n += 32) {
+            const float4 r = rows[n];
+            const float S = pc[__float_as_int(r.z)];
+            acc -= S >= 6.0f ? lgamma_joint(S, r.x, r.y) : lgamma_shift(S, r.x, r.y) - lgamma_pos(S);
+        }
+        lp += (double)acc;
+    }
+    {
+        // When some concentration is >= c_joint (warp-uniform flag), the elements of those pairs take the joint
+        // cancellation-free form, which also carries the -lgamma(c); otherwise the packed fast loop.
+        const bool fix = __any_sync(0xffffffffu, need_fix);
+        const float4* el = sp<float4>(t.el);
+        float acc = 0.0f;
+        if (!fix) {
+            f32x2 acc2 = dup2(0.0f);
+            int e = lane;
+#pragma unroll 1
+            for (; e + 32 < t.nbig; e += 64) {
+                const float4 va = el[e], vb = el[e + 32];
+                acc2 = add2(acc2, lgamma_shift_big2(pk2(pc[__float_as_int(va.z)], pc[__float_as_int(vb.z)]), pk2(va.x, vb.x),
+                                                    pk2(va.y, vb.y), pk2(va.w, vb.w)));
+            }
+            acc = lo2(acc2) + hi2(acc2);
+            if (e < t.nbig) {
+                const float4 v = el[e];
+                acc += lgamma_shift_big(pc[__float_as_int(v.z)], v.x, v.y);
+            }
+#pragma unroll 1
+            for (e = t.nbig + lane; e < t.NK; e += 32) {
+                const float4 v = el[e];
+                acc += lgamma_shift(pc[__float_as_int(v.z)], v.x, v.y);
+            }
+        } else {
+#pragma unroll 1
+            for (int e = lane; e < t.NK; e += 32) {
+                const float4 v = el[e];
+                const float cc = pc[__float_as_int(v.z)];
+                acc += cc >= c_joint ? lgamma_joint(cc, v.x, v.y) : lgamma_shift(cc, v.x, v.y);
+            }
+        }
+        lp += (double)acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    lp += t.lconst;
+    if (neg_sigma) lp = -CUDART_INF;   // HalfCauchy support [TFP]
+    return lp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : 4)) hmc_mg_kernel(const __grid_constant__ KArgs a) {
+    using T = float;
+    const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
+    const int cpc = blockDim.x >> 5;
+    const int ctas_per_ds = (a.C + cpc - 1) / cpc;
+    const int b = blockIdx.x / ctas_per_ds;
+    const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
+    const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P;
+    const int UPmax = (a.Umax + 1) >> 1;
+    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, a.NT, a.NOT);
+    MgTile tile;
+    mg_stage(a, b, pl, UPmax, tile);
+    if (c >= a.C) return;
+    const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
+    const uint32_t pc_off = pin_u32(chain_off + (uint32_t)pl.pc);
+    T* const vec = sp<T>(pin_u32(chain_off + (uint32_t)pl.vec));   // one flat state vector: momentum transpose, carry in / out
+    const size_t chain = (size_t)b * a.C + c;
+    const RngKey key{(uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), a.chain_id0 + (uint32_t)chain};
+    const int ref = a.ref[b];
+
+    MgLane ln;
+    ln.K = K;
+    ln.has = lane < K;
+    ln.active = ln.has && lane != ref;
+    // flat indices of the lane's parameters (order of scCODA_model.py:692-693): sigma_d[D] | b_offset[D][K-1] |
+    // ind_raw[D][K-1] | alpha[K]
+    const int jj = lane - (lane > ref);
+    const int ix_b = D + jj, ix_i = D + D * K1 + jj, ix_a = D + 2 * D * K1 + lane;
+
+    auto gather = [&](const T* v) {               // flat shared-memory vector -> lane registers
+        MgVec<D> r;
+        r.a = ln.has ? v[ix_a] : T(0);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            r.s[d] = v[d];
+            r.b[d] = ln.active ? v[ix_b + d * K1] : T(0);
+            r.i[d] = ln.active ? v[ix_i + d * K1] : T(0);
+        }
+        return r;
+    };
+    auto scatter = [&](T* v, const MgVec<D>& r) {    // lane registers -> flat vector (shared or global)
+        if (ln.has) v[ix_a] = r.a;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (lane == 0) v[d] = r.s[d];
+            if (ln.active) {
+                v[ix_b + d * K1] = r.b[d];
+                v[ix_i + d * K1] = r.i[d];
+            }
+        }
+    };
+
+    Adapt<T> ad;
+    load_chain_state<T>(a, chain, vec, ad, lane, 32);
+    __syncwarp();
+    MgVec<D> thc = gather(vec);                    // current state
+    MgVec<D> gc = mg_zero<D>();                    // its gradient
+    const int L = a.num_leapfrog;
+    const double log_target = log(a.target_accept);
+    T* draws = static_cast<T*>(a.draws) + chain * (size_t)a.num_results * P;
+    T* stats = static_cast<T*>(a.stats) + chain * (size_t)a.num_results * SCCODA_NSTAT;
+
+    // Transition t = step_begin - 1 is a pseudo-step that only evaluates the starting point (value + gradient)
+    // and "accepts" it: the hot loop contains one gradient and one value call site.
+    double lp_cur = 0.0;
+#pragma unroll 1
+    for (int t = a.step_begin - 1; t < a.step_end; ++t) {
+        const bool boot = t < a.step_begin;
+        const T eps = ad.eps;
+        T kin = T(0);
+        MgVec<D> q = thc, m = mg_zero<D>();
+        if (!boot) {
+            // momentum draw in the flat parameter order (the stream contract of philox.cuh), regrouped by cell type
+            __syncwarp();
+#pragma unroll 1
+            for (int i = lane; i < P; i += 32) {
+                const T p = frozen_param(a.dm, i) ? T(0) : rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
+                kin += p * p;
+                vec[i] = p;
+            }
+            __syncwarp();
+            // first half kick and first drift: q1 = q0 + eps (p + eps/2 grad(q0))
+            m = gather(vec);
+            mg_axpy<D>(m, T(0.5) * eps, gc);
+            mg_axpy<D>(q, eps, m);
+        }
+        const int nl = boot ? 1 : L;
+        MgVec<D> gr;
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l) {
+            gr = mg_grad<D>(tile, ln, q, pc_off, lane);
+            if (a.dm.freeze) {                     // SimpleModel: sigma_d and ind_raw stay where they are
+#pragma unroll
+                for (int d = 0; d < D; ++d) gr.s[d] = gr.i[d] = T(0);
+            }
+            if (!boot) {
+                const bool last = (l == nl - 1);
+                mg_axpy<D>(m, last ? T(0.5) * eps : eps, gr);
+                if (!last) mg_axpy<D>(q, eps, m);
+            }
+        }
+        // value at the end point, from the concentrations of the last gradient evaluation; priors (:703-741), the
+        // theta-independent constants live in lconst, parameters a lane does not own are zero
+        float prior = q.a * q.a * -0.02f, slab = 0.0f, cauchy = 0.0f;
+        bool neg_sigma = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            slab += fmaf(q.b[d], q.b[d], q.i[d] * q.i[d]);
+            if (q.s[d] >= 0.0f) cauchy += log1pf(q.s[d] * q.s[d]);
+            else neg_sigma = true;
+        }
+        prior = fmaf(-0.5f, slab, prior);
+        if (lane == 0) prior -= cauchy;
+        const double lp_new = mg_value(tile, pc_off, ln.has, prior, neg_sigma, K, lane);
+        bool acc = true;
+        double lar = 0.0;
+        if (!boot) {
+            // kinetic energies: the momenta of sigma_d are replicated, count them once
+            float k1 = m.a * m.a, ks = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                k1 += fmaf(m.b[d], m.b[d], m.i[d] * m.i[d]);
+                ks = fmaf(m.s[d], m.s[d], ks);
+            }
+            kin -= k1;
+            if (lane == 0) kin -= ks;
+            double dkin = (double)kin;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dkin += __shfl_xor_sync(0xffffffffu, dkin, o);
+            // [TFP] log_accept_ratio = safe_sum([logp', -logp, kinetic - kinetic']); non-finite -> -inf
+            lar = lp_new - lp_cur + 0.5 * dkin;
+            if (!isfinite(lar)) lar = -CUDART_INF;
+            const T u = rng_uniform<T>(key, 0u, (uint32_t)t, STREAM_ACCEPT);
+            acc = (double)logf((float)u) < lar;   // u is a 24-bit uniform, exact in fp32
+        }
+        if (acc) {
+            thc = q;
+            gc = gr;
+            lp_cur = lp_new;
+        }
+        if (boot) continue;
+        T traced_eps = eps;
+        if (a.method == SCCODA_METHOD_HMC) {
+            ad.simple(lar, t, a.num_adapt, log_target);
+        } else {
+            ad.dual(fmin(lar, 0.0), a.num_adapt, (T)a.target_accept);
+            traced_eps = t_exp(ad.log_avg);  // scCODA_model.py:408,419
+        }
+        const int r = t - a.num_burnin;
+        if (r >= 0 && a.store_draws) {
+            scatter(draws + (size_t)r * P, thc);
+            if (lane == 0)
+                write_stats<T>(stats + (size_t)r * SCCODA_NSTAT, lp_cur, lar, acc, traced_eps, lar < -1000.0, L,
+                               CUDART_NAN, false);
+        }
+    }
+    __syncwarp();
+    scatter(vec, thc);
+    __syncwarp();
+    store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
+}
+
+}  // namespace sccoda

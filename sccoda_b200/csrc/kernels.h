@@ -7,7 +7,11 @@
 
 namespace sccoda {
 
-enum { KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2, KIND_HMC_CC = 3, KIND_NUTS_CC = 4 /* case/control specialisations, hmc_cc.cuh */ };
+enum {
+    KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2,
+    KIND_HMC_CC = 3, KIND_NUTS_CC = 4,   // case/control specialisations (hmc_cc.cuh)
+    KIND_HMC_MG = 5                      // up to 8 covariate groups, D <= 3 on the same lane-per-cell-type layout (hmc_mg.cuh)
+};
 
 }  // namespace sccoda
 
@@ -130,11 +134,39 @@ __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT, int n_s
     return p;
 }
 
+// Shared-memory plan of the multi-group HMC kernel (hmc_mg.cuh): the arrays of CcPlan, one block per PAIR of groups
+// (UP = pairs of groups of the fullest dataset), plus the covariate values and row counts of the groups.
+struct MgPlan {
+    size_t cf, yv, ov, rows, el, xg, cnt, bounds, red, data_total;   // per CTA
+    size_t pc, vec, chain_total;                                      // per chain (relative)
+};
+constexpr int kMgMaxGroups = 8, kMgMaxD = 3;
+__host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NT, int NOT) {
+    MgPlan p;
+    size_t o = 0;
+    p.cf = o; o += (size_t)UP * 6 * 32 * 8;                      // f32x2[UP][6][32] rational coefficients
+    p.yv = o; o += (size_t)UP * NT * kItemR * 32 * 8;            // f32x2[UP][NT][R][32] item counts
+    p.ov = o; o += (size_t)UP * NOT * 32 * 8;                    // f32x2[UP][NOT][32] odd counts
+    p.rows = o; o += (size_t)N * 16;                             // (row total, host-like constant, slot of S_u, -)
+    p.el = o; o += (size_t)N * K * 16;                           // (count, host constant, concentration slot, 1/count)
+    p.xg = o; o += rnd16((size_t)UP * D * 8);                    // f32x2[UP][D] covariate values of the groups
+    p.cnt = o; o += rnd16((size_t)UP * 2 * 4);                   // float[2 UP] rows per group
+    p.bounds = o; o += rnd16((size_t)(2 * UP + 1) * 4);          // int: items / odd counts per group pair, big elements
+    p.red = o; o += 32;                                          // double[4]: staging reduction
+    p.data_total = o;
+    const size_t P = (size_t)D + 2 * (size_t)D * (K - 1) + K;
+    p.pc = 0;                                                    // float[2 UP][32] concentrations, slot u*32 + column
+    p.vec = (size_t)UP * 256;                                    // flat state vector
+    p.chain_total = p.vec + rnd16(P * 4);
+    return p;
+}
+
 int nvec_for(int kind, int max_depth);
 // KIND_HMC -> KIND_HMC_CC when the problem has the case/control shape the specialised kernel is written for
 int select_kind(const KArgs& a, int kind, int dtype, int W);
 cudaError_t launch_hmc_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t launch_nuts_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_hmc_mg(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int dtype);
 cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const KArgs& a, cudaStream_t st);
 cudaError_t launch_kernel_f32(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);

@@ -41,7 +41,7 @@ class SampleOutput:
     grid: int
     smem_bytes: int
     launches: int
-    kernel_kind: int = 0   # 1 generic HMC, 2 NUTS, 3 case/control HMC (include/sccoda_b200.h: sccoda_kernel_kind)
+    kernel_kind: int = 0   # 1 generic HMC, 2 NUTS, 3 / 4 case/control HMC / NUTS, 5 multi-group HMC (include/sccoda_b200.h: sccoda_kernel_kind)
 
     def stat(self, name: str):
         return self.stats[..., nat.STAT_NAMES.index(name)]

@@ -244,6 +244,149 @@ def test_case_control_kernel_ragged_batches():
     assert pk.NT >= 6 and pk.NOT >= 2 and int(pk.U.min()) == 1 and int(pk.U.max()) == 2
 
 
+def _design(kind, N, rs):
+    """Design matrices with more than two covariate groups."""
+    if kind == "levels3":                      # one covariate with three levels: D = 1, 3 groups
+        return rs.randint(0, 3, size=(N, 1)).astype(float)
+    if kind == "factorial2x2":                 # D = 2, 4 groups
+        return rs.randint(0, 2, size=(N, 2)).astype(float)
+    if kind == "conditions4":                  # one-hot coded four conditions (the Haber design): D = 3, 4 groups
+        lv = np.arange(N) % 4
+        return (lv[:, None] == np.arange(1, 4)[None, :]).astype(float)
+    if kind == "factorial2x2x2":               # D = 3, 8 groups
+        x = ((np.arange(N)[:, None] >> np.arange(3)[None, :]) & 1).astype(float)
+        return x[rs.permutation(N)]
+    if kind == "groups3_d2":                   # D = 2, 3 groups (odd group count: one empty slot in the last pair)
+        lv = np.arange(N) % 3
+        return np.stack([lv == 1, lv == 2], axis=1).astype(float)
+    raise ValueError(kind)
+
+
+def _multi_group_dataset(seed, kind, N, K, zero_frac=0.0):
+    rs = np.random.RandomState(seed)
+    x = _design(kind, N, rs)
+    D = x.shape[1]
+    b = rs.uniform(-2, 2, size=K)
+    w = np.zeros((D, K))
+    for d in range(D):
+        w[d, rs.randint(K - 1)] = rs.choice([-1.0, 0.7, 1.2])
+    logits = x @ w + b + np.sqrt(0.05) * rs.randn(N, K)
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    y = np.stack([rs.multinomial(3000, p[n]) for n in range(N)]).astype(float)
+    if zero_frac:
+        y[rs.rand(N, K) < zero_frac] = 0.0
+    return x, y
+
+
+def _mg_vs_generic(xs, ys, refs, method=0, C=2, steps=12, seed=4):
+    from oracle import np_oracle as o
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    B, K, D = len(xs), ys[0].shape[1], xs[0].shape[1]
+    pk = pack(np.stack(xs), np.stack(ys), np.asarray(refs), dtype=np.float32)
+    assert pk.grouped == 1                     # few covariate groups: the packer chooses the pair / item layout
+    prob = DeviceProblem(pk, chains=C)
+    init = _init(np.random.RandomState(seed), D, K, B * C).reshape(B, C, -1) * 0.5
+    init[..., :D] = 1.0
+    outs = [prob.sample(init, prob.make_sampler(method, steps, 0, num_adapt=steps, seed=seed, warps_per_chain=1,
+                                                generic_only=g)) for g in (True, False)]
+    assert outs[0].kernel_kind == 1 and outs[1].kernel_kind == 5
+    d = outs[1].draws.double().cpu().numpy()
+    lp = outs[1].stat("target_log_prob").double().cpu().numpy()
+    assert np.isfinite(d).all() and np.isfinite(lp).all()
+    # the traced log-density is the oracle's log-density at the traced state
+    for b in range(B):
+        m = o.prepare(xs[b], ys[b], int(refs[b]))
+        for c in range(C):
+            ref = np.array([o.logp(d[b, c, i], m) for i in range(steps)])
+            assert np.abs(lp[b, c] - ref).max() < 5e-6 * np.abs(ref).max() + 4e-3, (b, c, np.abs(lp[b, c] - ref).max())
+    # same Philox streams, same arithmetic per parameter: the first transitions agree with the generic kernel
+    n = min(steps, 5) if method == 0 else 2
+    assert np.abs(outs[0].draws.cpu().numpy()[:, :, :n] - outs[1].draws.cpu().numpy()[:, :, :n]).max() < 2e-3
+    assert np.array_equal(outs[0].stat("is_accepted").cpu().numpy()[:, :, :n],
+                          outs[1].stat("is_accepted").cpu().numpy()[:, :, :n])
+    assert np.allclose(outs[0].stat("step_size").cpu().numpy()[:, :, :n],
+                       outs[1].stat("step_size").cpu().numpy()[:, :, :n], rtol=1e-3)
+    return outs, pk, prob, init
+
+
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("kind", ["levels3", "factorial2x2", "conditions4", "factorial2x2x2", "groups3_d2"])
+def test_multi_group_kernel_follows_generic_kernel(kind, method):
+    """The lane-per-cell-type kernel for up to 8 covariate groups and D <= 3 (hmc_mg.cuh) against the generic kernel and
+    the oracle's log-density, on designs with 3, 4 and 8 groups."""
+    K = 9
+    xs, ys = zip(*[_multi_group_dataset(80 + b, kind, N=24, K=K, zero_frac=0.1 * (b == 1)) for b in range(3)])
+    outs, pk, prob, init = _mg_vs_generic(xs, ys, [K - 1, 0, 4], method=method)
+    assert 2 < pk.Umax <= 8
+    # chunked resume is bit-identical to the single launch
+    smp = prob.make_sampler(method, 12, 0, num_adapt=12, seed=4, warps_per_chain=1)
+    many = prob.sample(init, smp, chunk=5)
+    assert many.launches > 1 and np.array_equal(many.draws.cpu().numpy(), outs[1].draws.cpu().numpy())
+
+
+def test_multi_group_kernel_ragged_batch_and_cell_type_range():
+    """One batch whose datasets have 4, 3, 2 and 1 covariate groups (the batch-wide layout is padded to 4), with
+    pseudocounts, and the largest cell-type count the kernel takes (K = 31)."""
+    N = 16
+    xs, ys = [], []
+    for b, kind in enumerate(["conditions4", "conditions4", "conditions4", "conditions4"]):
+        x, y = _multi_group_dataset(90 + b, kind, N=N, K=31, zero_frac=0.15 if b == 2 else 0.0)
+        if b == 1:
+            x[x[:, 2] == 1] = 0.0              # three groups
+        if b == 2:
+            x[:, 1:] = 0.0                     # two groups
+        if b == 3:
+            x[:] = 0.0                         # a single group
+        xs.append(x)
+        ys.append(y)
+    outs, pk, _, _ = _mg_vs_generic(xs, ys, [30, 0, 7, 12], C=3, steps=8)
+    assert sorted(pk.U.tolist()) == [1, 2, 3, 4] and pk.NOT >= 1
+
+
+def test_multi_group_kernel_frozen_spike_slab():
+    """SimpleModel semantics (sigma_d and ind_raw frozen) on the multi-group kernel."""
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    K = 6
+    x, y = _multi_group_dataset(5, "factorial2x2", N=20, K=K)
+    prob = DeviceProblem(pack(x[None], y[None], np.array([K - 1]), dtype=np.float32), chains=4)
+    init = _init(np.random.RandomState(2), 2, K, 4).reshape(1, 4, -1) * 0.3
+    init[..., :2] = 1.0
+    init[..., 2 + 2 * (K - 1):2 + 4 * (K - 1)] = 0.7
+    outs = [prob.sample(init, prob.make_sampler(0, 30, 0, num_adapt=30, seed=9, warps_per_chain=1, generic_only=g,
+                                                freeze_spike_slab=True)) for g in (True, False)]
+    assert outs[1].kernel_kind == 5
+    d = outs[1].draws.cpu().numpy()
+    assert np.all(d[..., :2] == 1.0) and np.all(d[..., 2 + 2 * (K - 1):2 + 4 * (K - 1)] == np.float32(0.7))
+    assert np.abs(outs[0].draws.cpu().numpy()[:, :, :5] - d[:, :, :5]).max() < 2e-3
+
+
+def test_fp32_statistical_parity_multi_group():
+    """Posterior means and accept rates of the multi-group kernel against the generic kernel over many chains."""
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    K, C = 6, 256
+    x, y = _multi_group_dataset(12, "conditions4", N=16, K=K)
+    prob = DeviceProblem(pack(x[None], y[None], np.array([K - 1]), dtype=np.float32), chains=C)
+    init = np.zeros((1, C, 3 + 6 * (K - 1) + K), np.float32)
+    init[..., :3] = 1.0
+    init[..., 3:3 + 3 * (K - 1)] = np.random.RandomState(0).randn(C, 3 * (K - 1))
+    res = []
+    for g in (True, False):
+        out = prob.sample(init, prob.make_sampler(0, 1500, 500, seed=21, warps_per_chain=1, generic_only=g))
+        assert out.kernel_kind == (1 if g else 5)
+        d = out.draws.double().cpu().numpy()[0, :, 500:]
+        acc = out.stat("is_accepted").double().cpu().numpy()[0].mean()
+        res.append((d.mean(axis=1), acc))
+    (m0, a0), (m1, a1) = res
+    assert abs(a0 - a1) < 0.02
+    se = np.sqrt(m0.var(axis=0) / C + m1.var(axis=0) / C)
+    z = np.abs(m0.mean(axis=0) - m1.mean(axis=0)) / np.maximum(se, 1e-6)
+    assert z.max() < 5.0, z.max()
+
+
 def test_case_control_nuts_kernel_follows_generic_kernel():
     """Same Philox streams, same tree logic: the lane-per-cell-type NUTS kernel and the generic NUTS kernel build the
     same trees for the first transitions in fp32 (later, rounding differences change a U-turn decision somewhere)."""
