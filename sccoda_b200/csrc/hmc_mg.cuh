@@ -263,6 +263,22 @@ __device__ __forceinline__ MgVec<D> mg_grad(const MgTile& t, const MgLane& ln, c
     return g;
 }
 
+// lane's share of the parameter priors (:703-741) and the HalfCauchy support flag, for mg_value
+template <int D>
+__device__ __forceinline__ float mg_prior(const MgVec<D>& q, int lane, bool& neg_sigma) {
+    float prior = q.a * q.a * -0.02f, slab = 0.0f, cauchy = 0.0f;
+    neg_sigma = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        slab += fmaf(q.b[d], q.b[d], q.i[d] * q.i[d]);
+        if (q.s[d] >= 0.0f) cauchy += log1pf(q.s[d] * q.s[d]);
+        else neg_sigma = true;
+    }
+    prior = fmaf(-0.5f, slab, prior);
+    if (lane == 0) prior -= cauchy;
+    return prior;
+}
+
 // Value of the log-density from the concentrations the last gradient evaluation left in pc (same terms, guards and
 // precision strategy as cc_value / dm_value); `prior` is the lane's share of the parameter priors.
 static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off, bool has, float prior, bool neg_sigma, int K, int lane) {
@@ -352,7 +368,7 @@ __global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : 4)) hmc_mg_ker
     const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
     const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P;
     const int UPmax = (a.Umax + 1) >> 1;
-    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, a.NT, a.NOT);
+    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, a.NT, a.NOT, 0);
     MgTile tile;
     mg_stage(a, b, pl, UPmax, tile);
     if (c >= a.C) return;
@@ -446,16 +462,8 @@ __global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : 4)) hmc_mg_ker
         }
         // value at the end point, from the concentrations of the last gradient evaluation; priors (:703-741), the
         // theta-independent constants live in lconst, parameters a lane does not own are zero
-        float prior = q.a * q.a * -0.02f, slab = 0.0f, cauchy = 0.0f;
-        bool neg_sigma = false;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            slab += fmaf(q.b[d], q.b[d], q.i[d] * q.i[d]);
-            if (q.s[d] >= 0.0f) cauchy += log1pf(q.s[d] * q.s[d]);
-            else neg_sigma = true;
-        }
-        prior = fmaf(-0.5f, slab, prior);
-        if (lane == 0) prior -= cauchy;
+        bool neg_sigma;
+        const float prior = mg_prior<D>(q, lane, neg_sigma);
         const double lp_new = mg_value(tile, pc_off, ln.has, prior, neg_sigma, K, lane);
         bool acc = true;
         double lar = 0.0;
@@ -501,6 +509,273 @@ __global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : 4)) hmc_mg_ker
     }
     __syncwarp();
     scatter(vec, thc);
+    __syncwarp();
+    store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3mg — NUTS for the same designs: the iterative tree of nuts_kernel / nuts_cc_kernel ([TFP] NoUTurnSampler.one_step as
+// restated in SURVEY §8c) on the lane-per-cell-type state.  A stored vector of the tree is D float4 per lane
+// (3 D + 1 parameters) in shared memory; the leaf being integrated lives in registers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mg_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int D>
+__device__ __forceinline__ MgVec<D> mg_ld(const float4* slot) {
+    float f[4 * D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const float4 v = slot[32 * k];
+        f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+    }
+    MgVec<D> r;
+    r.a = f[0];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        r.b[d] = f[1 + d];
+        r.i[d] = f[1 + D + d];
+        r.s[d] = f[1 + 2 * D + d];
+    }
+    return r;
+}
+template <int D>
+__device__ __forceinline__ void mg_st(float4* slot, const MgVec<D>& r) {
+    float f[4 * D];
+#pragma unroll
+    for (int k = 0; k < 4 * D; ++k) f[k] = 0.0f;
+    f[0] = r.a;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        f[1 + d] = r.b[d];
+        f[1 + D + d] = r.i[d];
+        f[1 + 2 * D + d] = r.s[d];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) slot[32 * k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+}
+// per-lane part of a dot product over the flat parameter vector (sigma_d is replicated: lane 0 counts it)
+template <int D>
+__device__ __forceinline__ float mg_dot(const MgVec<D>& x, const MgVec<D>& y, int lane) {
+    float v = x.a * y.a, sv = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        v = fmaf(x.b[d], y.b[d], fmaf(x.i[d], y.i[d], v));
+        sv = fmaf(x.s[d], y.s[d], sv);
+    }
+    return lane == 0 ? v + sv : v;
+}
+template <int D>
+__global__ void __launch_bounds__(128, D == 1 ? 4 : (D == 2 ? 3 : 2)) nuts_mg_kernel(const __grid_constant__ KArgs a) {
+    using T = float;
+    using V = MgVec<D>;
+    const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
+    const int cpc = blockDim.x >> 5;
+    const int ctas_per_ds = (a.C + cpc - 1) / cpc;
+    const int b = blockIdx.x / ctas_per_ds;
+    const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
+    const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P, maxd = a.max_depth;
+    const int UPmax = (a.Umax + 1) >> 1;
+    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, a.NT, a.NOT, 11 + 2 * (maxd + 1));
+    MgTile tile;
+    mg_stage(a, b, pl, UPmax, tile);
+    if (c >= a.C) return;
+    const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
+    const uint32_t pc_off = pin_u32(chain_off + (uint32_t)pl.pc);
+    T* const vec = sp<T>(pin_u32(chain_off + (uint32_t)pl.vec));
+    float4* const slots = sp<float4>(pin_u32(chain_off + (uint32_t)pl.slots)) + lane;   // slot k of this lane: slot(k)
+    auto slot = [&](int k) { return slots + 32 * D * k; };
+    enum { S_CQ = 0, S_CG, S_LQ, S_LP, S_LG, S_RQ, S_RP, S_RG, S_SQ, S_SG, S_RHO, S_CKP };
+    const int S_CKR = S_CKP + (maxd + 1);
+    const size_t chain = (size_t)b * a.C + c;
+    const RngKey key{(uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), a.chain_id0 + (uint32_t)chain};
+    const int ref = a.ref[b];
+
+    MgLane ln;
+    ln.K = K;
+    ln.has = lane < K;
+    ln.active = ln.has && lane != ref;
+    const int jj = lane - (lane > ref);
+    const int ix_b = D + jj, ix_i = D + D * K1 + jj, ix_a = D + 2 * D * K1 + lane;
+    auto gather = [&](const T* v) {
+        V r;
+        r.a = ln.has ? v[ix_a] : T(0);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            r.s[d] = v[d];
+            r.b[d] = ln.active ? v[ix_b + d * K1] : T(0);
+            r.i[d] = ln.active ? v[ix_i + d * K1] : T(0);
+        }
+        return r;
+    };
+    auto scatter = [&](T* v, const V& r) {
+        if (ln.has) v[ix_a] = r.a;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (lane == 0) v[d] = r.s[d];
+            if (ln.active) {
+                v[ix_b + d * K1] = r.b[d];
+                v[ix_i + d * K1] = r.i[d];
+            }
+        }
+    };
+
+    Adapt<T> ad;
+    load_chain_state<T>(a, chain, vec, ad, lane, 32);
+    __syncwarp();
+    V q = gather(vec), p = mg_zero<D>(), gq = mg_zero<D>(), rho_s = mg_zero<D>();
+    T* draws = static_cast<T*>(a.draws) + chain * (size_t)a.num_results * P;
+    T* stats = static_cast<T*>(a.stats) + chain * (size_t)a.num_results * SCCODA_NSTAT;
+
+    // t = step_begin - 1: pseudo-transition that evaluates the starting point through the same (single) call site of
+    // the gradient / value as the leaves of the trees.
+    double lp_cur = 0.0;
+#pragma unroll 1
+    for (int t = a.step_begin - 1; t < a.step_end; ++t) {
+        const bool boot = t < a.step_begin;
+        const T eps = ad.eps;
+        double e0 = 0.0;
+        if (!boot) {
+            T kin = T(0);
+            __syncwarp();
+#pragma unroll 1
+            for (int i = lane; i < P; i += 32) {
+                const T pm = frozen_param(a.dm, i) ? T(0) : rng_normal<T>(key, (uint32_t)i, (uint32_t)t);
+                kin += pm * pm;
+                vec[i] = pm;
+            }
+            __syncwarp();
+            const V pm = gather(vec), cq = mg_ld<D>(slot(S_CQ)), cg = mg_ld<D>(slot(S_CG));
+            mg_st<D>(slot(S_LQ), cq); mg_st<D>(slot(S_LP), pm); mg_st<D>(slot(S_LG), cg);
+            mg_st<D>(slot(S_RQ), cq); mg_st<D>(slot(S_RP), pm); mg_st<D>(slot(S_RG), cg);
+            mg_st<D>(slot(S_RHO), pm);
+            e0 = lp_cur - 0.5 * mg_sum_d((double)kin);
+        }
+        double l_lp = lp_cur, r_lp = lp_cur, c_lp = lp_cur, c_energy = e0, s_lp = lp_cur, s_en = e0;
+        double wsum = 0.0, accept_sum = 0.0;
+        int leapfrogs = 0, depth = 0;
+        bool is_acc = false, cont = true, not_div = true;
+        uint32_t leaf_serial = 0;
+        const int depth_limit = boot ? 1 : maxd;
+#pragma unroll 1
+        while (depth < depth_limit && cont) {
+            const bool forward = boot ? true : (rng_bit(key, (uint32_t)depth, (uint32_t)t, STREAM_NUTS_DIR) != 0u);
+            const int e_q = forward ? S_RQ : S_LQ, e_p = forward ? S_RP : S_LP, e_g = forward ? S_RG : S_LG;
+            const T se = forward ? eps : -eps;
+            double lqv = forward ? r_lp : l_lp;
+            if (!boot) {
+                q = mg_ld<D>(slot(e_q));
+                p = mg_ld<D>(slot(e_p));
+                gq = mg_ld<D>(slot(e_g));
+                rho_s = mg_zero<D>();
+            }
+            const unsigned n_leaves = 1u << depth;
+            double w_s = -CUDART_INF;
+            bool alive = true;
+#pragma unroll 1
+            for (unsigned leaf = 0; leaf < n_leaves && alive; ++leaf) {
+                if (!boot) {
+                    mg_axpy<D>(p, T(0.5) * se, gq);
+                    mg_axpy<D>(q, se, p);
+                }
+                gq = mg_grad<D>(tile, ln, q, pc_off, lane);
+                if (a.dm.freeze) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) gq.s[d] = gq.i[d] = T(0);
+                }
+                {
+                    bool neg_sigma;
+                    const float prior = mg_prior<D>(q, lane, neg_sigma);
+                    lqv = mg_value(tile, pc_off, ln.has, prior, neg_sigma, K, lane);
+                }
+                if (boot) break;
+                mg_axpy<D>(p, T(0.5) * se, gq);
+                mg_axpy<D>(rho_s, T(1), p);
+                const T kk = mg_dot<D>(p, p, lane);
+                leapfrogs += 1;
+                const int idx_max = __popc(leaf >> 1);
+                bool no_uturn = true;
+                if ((leaf & 1u) == 0u) {
+                    mg_st<D>(slot(S_CKP + idx_max), p);
+                    mg_st<D>(slot(S_CKR + idx_max), rho_s);
+                } else {
+                    const int n_chk = __ffs(~leaf) - 1;  // trailing ones
+#pragma unroll 1
+                    for (int sidx = idx_max; sidx > idx_max - n_chk && no_uturn; --sidx) {
+                        const V cp = mg_ld<D>(slot(S_CKP + sidx));
+                        V span = mg_ld<D>(slot(S_CKR + sidx));
+                        // span = rho_s - checkpoint rho + checkpoint momentum
+                        span.a = rho_s.a - span.a + cp.a;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            span.b[d] = rho_s.b[d] - span.b[d] + cp.b[d];
+                            span.i[d] = rho_s.i[d] - span.i[d] + cp.i[d];
+                            span.s[d] = rho_s.s[d] - span.s[d] + cp.s[d];
+                        }
+                        const double D1 = mg_sum_d((double)mg_dot<D>(span, cp, lane)), D2 = mg_sum_d((double)mg_dot<D>(span, p, lane));
+                        if (!(D1 >= 0.0 && D2 >= 0.0)) no_uturn = false;
+                    }
+                }
+                double energy = lqv - 0.5 * mg_sum_d((double)kk);
+                if (isnan(energy)) energy = -CUDART_INF;
+                const double delta = energy - e0;
+                const bool divergent = !(-delta < 1000.0);
+                const double w_new = logaddexp_d(w_s, delta);
+                const double u = (double)rng_uniform<T>(key, leaf_serial++, (uint32_t)t, STREAM_NUTS_LEAF);
+                const double thresh = (w_new > -CUDART_INF) ? delta - w_new : CUDART_NAN;
+                if (log1p(-u) <= thresh) {
+                    mg_st<D>(slot(S_SQ), q);
+                    mg_st<D>(slot(S_SG), gq);
+                    s_lp = lqv; s_en = energy;
+                }
+                w_s = w_new;
+                accept_sum += exp(fmin(delta, 0.0));
+                if (divergent) not_div = false;
+                alive = (!divergent) && no_uturn;
+            }
+            if (boot) {
+                mg_st<D>(slot(S_CQ), q);
+                mg_st<D>(slot(S_CG), gq);
+                c_lp = lqv;
+                break;
+            }
+            const double tree_w = alive ? w_s : -CUDART_INF;
+            double thresh = tree_w - wsum;
+            if (isnan(thresh)) thresh = 0.0;
+            const double u = (double)rng_uniform<T>(key, (uint32_t)depth, (uint32_t)t, STREAM_NUTS_TOP);
+            if ((log1p(-u) <= thresh) && alive) {
+                mg_st<D>(slot(S_CQ), mg_ld<D>(slot(S_SQ)));
+                mg_st<D>(slot(S_CG), mg_ld<D>(slot(S_SG)));
+                c_lp = s_lp; c_energy = s_en; is_acc = true;
+            }
+            wsum = logaddexp_d(wsum, tree_w);
+            mg_st<D>(slot(e_q), q);
+            mg_st<D>(slot(e_p), p);
+            mg_st<D>(slot(e_g), gq);
+            V rho = mg_ld<D>(slot(S_RHO));
+            mg_axpy<D>(rho, T(1), rho_s);
+            mg_st<D>(slot(S_RHO), rho);
+            const double D1 = mg_sum_d((double)mg_dot<D>(rho, mg_ld<D>(slot(S_LP)), lane));
+            const double D2 = mg_sum_d((double)mg_dot<D>(rho, mg_ld<D>(slot(S_RP)), lane));
+            if (forward) r_lp = lqv; else l_lp = lqv;
+            cont = alive && (D1 >= 0.0) && (D2 >= 0.0);
+            depth += 1;
+        }
+        lp_cur = c_lp;
+        if (boot) continue;
+        const double lar = accept_sum > 0.0 ? log(accept_sum / (double)leapfrogs) : -CUDART_INF;
+        ad.dual(fmin(lar, 0.0), a.num_adapt, (T)a.target_accept);
+        const int r = t - a.num_burnin;
+        if (r >= 0 && a.store_draws) {
+            scatter(draws + (size_t)r * P, mg_ld<D>(slot(S_CQ)));
+            if (lane == 0)
+                write_stats<T>(stats + (size_t)r * SCCODA_NSTAT, lp_cur, lar, is_acc, eps, !not_div, leapfrogs, c_energy, cont);
+        }
+    }
+    __syncwarp();
+    scatter(vec, mg_ld<D>(slot(S_CQ)));
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
 }

@@ -8,7 +8,7 @@ namespace sccoda {
 int nvec_for(int kind, int max_depth) {
     if (kind == KIND_LOGP) return 2;
     if (kind == KIND_HMC) return 6;
-    if (kind == KIND_HMC_CC || kind == KIND_NUTS_CC || kind == KIND_HMC_MG) return 1;
+    if (kind == KIND_HMC_CC || kind == KIND_NUTS_CC || kind == KIND_HMC_MG || kind == KIND_NUTS_MG) return 1;
     return 15 + 2 * (max_depth + 1);
 }
 
@@ -16,9 +16,9 @@ int select_kind(const KArgs& a, int kind, int dtype, int W) {
     if ((kind == KIND_HMC || kind == KIND_NUTS) && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 &&
         a.dm.D == 1 && a.Umax == 2 && a.dm.K <= 31)
         return kind == KIND_HMC ? KIND_HMC_CC : KIND_NUTS_CC;
-    if (kind == KIND_HMC && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 && a.dm.D <= kMgMaxD &&
-        a.Umax <= kMgMaxGroups && a.dm.K <= 31)
-        return KIND_HMC_MG;
+    if ((kind == KIND_HMC || kind == KIND_NUTS) && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 &&
+        a.dm.D <= kMgMaxD && a.Umax <= kMgMaxGroups && a.dm.K <= 31)
+        return kind == KIND_HMC ? KIND_HMC_MG : KIND_NUTS_MG;
     return kind;
 }
 
@@ -28,8 +28,9 @@ size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int d
         const CcPlan cp = plan_cc(a.dm.N, a.dm.K, a.NT, a.NOT, kind == KIND_NUTS_CC ? 11 + 2 * (a.max_depth + 1) : 0);
         return cp.data_total + (size_t)chains_per_cta * cp.chain_total;
     }
-    if (kind == KIND_HMC_MG) {
-        const MgPlan mp = plan_mg(a.dm.N, a.dm.K, a.dm.D, (a.Umax + 1) / 2, a.NT, a.NOT);
+    if (kind == KIND_HMC_MG || kind == KIND_NUTS_MG) {
+        const MgPlan mp = plan_mg(a.dm.N, a.dm.K, a.dm.D, (a.Umax + 1) / 2, a.NT, a.NOT,
+                                  kind == KIND_NUTS_MG ? 11 + 2 * (a.max_depth + 1) : 0);
         return mp.data_total + (size_t)chains_per_cta * mp.chain_total;
     }
     const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem ? a.el_count : 0, a.grouped ? a.NImax : 0, a.NF,
@@ -45,6 +46,7 @@ cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const 
     if (kind == KIND_HMC_CC) return launch_hmc_cc(a, grid, block, smem, st);
     if (kind == KIND_NUTS_CC) return launch_nuts_cc(a, grid, block, smem, st);
     if (kind == KIND_HMC_MG) return launch_hmc_mg(a, grid, block, smem, st);
+    if (kind == KIND_NUTS_MG) return launch_nuts_mg(a, grid, block, smem, st);
     if (a.grouped) {
         if (dtype == SCCODA_F64) return launch_kernel_f64g(kind, W, a, grid, block, smem, st);
         return launch_kernel_f32g(kind, W, a, grid, block, smem, st);

@@ -10,7 +10,7 @@ namespace sccoda {
 enum {
     KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2,
     KIND_HMC_CC = 3, KIND_NUTS_CC = 4,   // case/control specialisations (hmc_cc.cuh)
-    KIND_HMC_MG = 5                      // up to 8 covariate groups, D <= 3 on the same lane-per-cell-type layout (hmc_mg.cuh)
+    KIND_HMC_MG = 5, KIND_NUTS_MG = 6    // up to 8 covariate groups, D <= 3 on the same lane-per-cell-type layout (hmc_mg.cuh)
 };
 
 }  // namespace sccoda
@@ -138,10 +138,11 @@ __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT, int n_s
 // (UP = pairs of groups of the fullest dataset), plus the covariate values and row counts of the groups.
 struct MgPlan {
     size_t cf, yv, ov, rows, el, xg, cnt, bounds, red, data_total;   // per CTA
-    size_t pc, vec, chain_total;                                      // per chain (relative)
+    size_t pc, vec, slots, chain_total;                               // per chain (relative)
 };
 constexpr int kMgMaxGroups = 8, kMgMaxD = 3;
-__host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NT, int NOT) {
+// n_slots: stored vectors of the NUTS tree (D float4 per lane each; 0 for HMC)
+__host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NT, int NOT, int n_slots) {
     MgPlan p;
     size_t o = 0;
     p.cf = o; o += (size_t)UP * 6 * 32 * 8;                      // f32x2[UP][6][32] rational coefficients
@@ -157,7 +158,8 @@ __host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NT, i
     const size_t P = (size_t)D + 2 * (size_t)D * (K - 1) + K;
     p.pc = 0;                                                    // float[2 UP][32] concentrations, slot u*32 + column
     p.vec = (size_t)UP * 256;                                    // flat state vector
-    p.chain_total = p.vec + rnd16(P * 4);
+    p.slots = p.vec + rnd16(P * 4);                              // float4[n_slots][D][32]
+    p.chain_total = p.slots + (size_t)n_slots * D * 512;
     return p;
 }
 
@@ -167,6 +169,7 @@ int select_kind(const KArgs& a, int kind, int dtype, int W);
 cudaError_t launch_hmc_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t launch_nuts_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t launch_hmc_mg(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_nuts_mg(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int dtype);
 cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const KArgs& a, cudaStream_t st);
 cudaError_t launch_kernel_f32(int kind, int W, const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
