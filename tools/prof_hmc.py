@@ -28,11 +28,17 @@ ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--step-size", type=float, default=0.02)
 ap.add_argument("--generic", type=int, default=0, help="1: never take the case/control kernel")
 ap.add_argument("--grouped", type=int, default=-1, help="-1 auto, 0 element path, 1 pair/item path")
+ap.add_argument("--conditions", type=int, default=2, help="> 2: one-hot coded conditions (D = conditions - 1), n-per-group rows each")
 a = ap.parse_args()
 
-x, y, _ = generate_sweep(a.datasets, K=a.K, n_per_group=a.n_per_group)
+if a.conditions > 2:
+    x, y, _ = generate_sweep(a.datasets, K=a.K, n_per_group=a.conditions * a.n_per_group // 2)
+    lv = np.arange(y.shape[1]) % a.conditions
+    x = np.broadcast_to((lv[:, None] == np.arange(1, a.conditions)[None, :]).astype(float), (a.datasets, y.shape[1], a.conditions - 1)).copy()
+else:
+    x, y, _ = generate_sweep(a.datasets, K=a.K, n_per_group=a.n_per_group)
 pk = pack(x, y, a.K - 1, dtype=np.float32, grouped=None if a.grouped < 0 else bool(a.grouped))
-init = sch.initial_states(a.datasets, a.chains, 1, a.K, seed=1).astype(np.float32)
+init = sch.initial_states(a.datasets, a.chains, x.shape[2], a.K, seed=1).astype(np.float32)
 prob = DeviceProblem(pk, chains=a.chains)
 smp = prob.make_sampler(a.method, a.results, a.burnin, step_size=a.step_size, seed=3, warps_per_chain=a.W, chains_per_cta=a.cpc, generic_only=bool(a.generic))
 for _ in range(a.reps):
