@@ -176,6 +176,16 @@ int sccoda_sample(const sccoda_problem* prob, const sccoda_sampler* smp, const v
 int sccoda_summarize(const sccoda_problem* prob, int32_t num_results, int32_t skip, const void* draws,
                      const void* stats, double* summary, void* stream);
 
+/* Posterior-predictive quantities per stored draw, straight from device-resident draws — replaces the per-draw
+ * python loops of get_y_hat (scCODA_model.py:806-827).  For the draws s in [draw_begin, draw_end) of every chain:
+ *   concentration[b,c,s-draw_begin,n,k] = exp(alpha_k + x_n . beta_k),  beta = sigmoid(50 ind_raw) sigma_d b_offset
+ *   prediction   [b,c,s-draw_begin,n,k] = n_total_n * concentration / sum_k concentration   (DirichletMultinomial mean)
+ * Both outputs have the problem's dtype and shape [B,C,draw_end-draw_begin,N,K]; either may be NULL.
+ * row_order [B,N] (device, may be NULL): output row of each packed row — the packed rows are sorted by covariate
+ * group, row_order restores the caller's sample order (NULL: rows stay in packed order). */
+int sccoda_predict(const sccoda_problem* prob, const int32_t* row_order, int32_t num_results, int32_t draw_begin,
+                   int32_t draw_end, const void* draws, void* concentration, void* prediction, void* stream);
+
 /* Bytes of dynamic shared memory and threads per CTA the sampler would use (for planning / tests). */
 int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* warps_per_chain,
                        int32_t* chains_per_cta, int32_t* grid, int32_t* smem_bytes);

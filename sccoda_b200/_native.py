@@ -20,7 +20,7 @@ STAT_NAMES = ("target_log_prob", "log_accept_ratio", "is_accepted", "step_size",
 NCARRY = 8
 NSUM_PARAM, NSUM_BETA, NSUM_SCALAR = 2, 4, 6
 
-EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sample", "sccoda_summarize",
+EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sample", "sccoda_summarize", "sccoda_predict",
            "sccoda_launch_plan", "sccoda_kernel_kind", "sccoda_sample_host", "sccoda_release_workspace", "sccoda_measure_peaks")
 
 
@@ -82,6 +82,7 @@ def lib() -> ctypes.CDLL:
         _lib.sccoda_logp_grad.argtypes = [pp, vp, vp, vp, vp]
         _lib.sccoda_sample.argtypes = [pp, sp, vp, vp, vp, vp, vp]
         _lib.sccoda_summarize.argtypes = [pp, i32, i32, vp, vp, vp, vp]
+        _lib.sccoda_predict.argtypes = [pp, vp, i32, i32, i32, vp, vp, vp, vp]
         _lib.sccoda_launch_plan.argtypes = [pp, sp] + [ctypes.POINTER(i32)] * 4
         _lib.sccoda_kernel_kind.argtypes = [pp, sp, ctypes.POINTER(i32)]
         _lib.sccoda_sample_host.argtypes = [pp, sp, vp, vp, vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float)]

@@ -279,6 +279,22 @@ int sccoda_summarize(const sccoda_problem* prob, int32_t num_results, int32_t sk
     return 0;
 }
 
+int sccoda_predict(const sccoda_problem* prob, const int32_t* row_order, int32_t num_results, int32_t draw_begin,
+                   int32_t draw_end, const void* draws, void* concentration, void* prediction, void* stream) {
+    int rc = validate(prob);
+    if (rc) return rc;
+    if (!draws || (!concentration && !prediction)) return fail(-32, "draws and at least one output must not be NULL");
+    if (draw_begin < 0 || draw_end > num_results || draw_begin >= draw_end)
+        return fail(-33, "need 0 <= draw_begin < draw_end <= num_results");
+    cudaError_t e = sccoda::launch_predict(prob->dtype, prob->B, prob->C, prob->N, prob->K, prob->D, prob->Umax, prob->ref, prob->xu,
+                                           prob->grp, prob->ntot, row_order, num_results, draw_begin, draw_end, draws, concentration,
+                                           prediction, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidConfiguration)
+        return fail(-9, "problem needs more shared memory per warp than the device has (Umax*K too large)");
+    CUDA_TRY(e);
+    return 0;
+}
+
 int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, const void* init, void* draws, void* stats,
                        double* summary, int32_t summary_skip, int32_t device, float* kernel_ms) {
     if (!ph || !smp || !init) return fail(-40, "NULL argument");

@@ -181,4 +181,9 @@ cudaError_t launch_kernel_f64g(int kind, int W, const KArgs& a, int grid, int bl
 cudaError_t launch_summary(int dtype, int B, int C, int N, int K, int D, const int* ref, int num_results, int skip,
                            const void* draws, const void* stats, double* summary, cudaStream_t st);
 
+// K5 (predict.cu)
+cudaError_t launch_predict(int dtype, int B, int C, int N, int K, int D, int Umax, const int* ref, const void* xu, const int* grp,
+                           const void* ntot, const int* order, int num_results, int lo, int hi, const void* draws, void* conc,
+                           void* pred, cudaStream_t st);
+
 }  // namespace sccoda

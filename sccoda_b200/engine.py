@@ -165,6 +165,25 @@ class DeviceProblem:
                                                  _ptr(out), stream), "sccoda_summarize")
         return out
 
+    def predict(self, draws, lo: int = 0, hi: Optional[int] = None, concentration: bool = True, prediction: bool = True):
+        """Posterior-predictive quantities of the draws [lo, hi) on device (K5, `sccoda_predict`): returns
+        (concentration, prediction), each [B,C,hi-lo,N,K] in the problem's dtype (rows in the caller's sample order)
+        or None when not requested."""
+        torch = _torch()
+        if getattr(self, "_row_order", None) is None:
+            self._row_order = torch.as_tensor(np.ascontiguousarray(self.packed.row_order, dtype=np.int32), device=self.device)
+        S = draws.shape[2]
+        hi = S if hi is None else int(hi)
+        shape = (self.B, self.C, hi - int(lo), self.N, self.K)
+        conc = torch.empty(shape, dtype=draws.dtype, device=self.device) if concentration else None
+        pred = torch.empty(shape, dtype=draws.dtype, device=self.device) if prediction else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            nat.check(nat.lib().sccoda_predict(ctypes.byref(self.c_problem), _ptr(self._row_order), S, int(lo), hi, _ptr(draws),
+                                               _ptr(conc) if concentration else None, _ptr(pred) if prediction else None,
+                                               stream), "sccoda_predict")
+        return conc, pred
+
     def split_summary(self, summ):
         """summary tensor/array [B,C,width] -> dict of named views."""
         P, DK = self.P, self.D * self.K

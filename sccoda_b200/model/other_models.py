@@ -83,18 +83,25 @@ class SimpleModel(dm.CompositionalModel):
 
         states, kernel_results, duration = self.sampling(num_results, num_burnin, kernel, init, trace_fn=trace_fn)
         states_burnin, sample_stats, acc_rate = self.get_chains_after_burnin(states, kernel_results, num_burnin)
-        y_hat = self.get_y_hat(states_burnin, num_results, num_burnin)
+        y_hat = self.get_y_hat(states_burnin, num_results, num_burnin, lazy=True)
+        self._last_out = None
         sampling_stats = {"chain_length": num_results, "num_burnin": num_burnin, "acc_rate": acc_rate,
                           "duration": duration, "y_hat": y_hat}
         return self.make_result(states_burnin, sample_stats, sampling_stats)
 
-    def get_y_hat(self, states_burnin: List[np.ndarray], num_results: int, num_burnin: int) -> np.ndarray:
+    def get_y_hat(self, states_burnin: List[np.ndarray], num_results: int, num_burnin: int, lazy: bool = False
+                  ) -> np.ndarray:
         """beta, concentration, prediction per draw are APPENDED to `states_burnin`; returns the posterior-mode count
-        matrix (other_models.py:222-282), vectorised."""
+        matrix (other_models.py:222-282), vectorised.  lazy=True: concentration / prediction are generated on the device
+        on first use (see scCODAModel.get_y_hat)."""
         b, alphas = states_burnin[:2]
         beta_ = np.insert(b, self.reference_cell_type, 0.0, axis=-1)                  # :257-261
-        conc_ = np.exp(np.einsum("nd,...dk->...nk", self.x, beta_) + alphas[..., None, :])      # :265-266
-        pred_ = self.n_total[:, None] * conc_ / conc_.sum(axis=-1, keepdims=True)     # :268-271 DirMult mean
+        lz = self._lazy_predictive(num_burnin, one_chain=alphas.ndim == 2) if lazy else None
+        if lz is not None and lz[0].shape[:-2] == alphas.shape[:-1]:
+            conc_, pred_ = lz
+        else:
+            conc_ = np.exp(np.einsum("nd,...dk->...nk", self.x, beta_) + alphas[..., None, :])      # :265-266
+            pred_ = self.n_total[:, None] * conc_ / conc_.sum(axis=-1, keepdims=True)     # :268-271 DirMult mean
         states_burnin.extend([beta_, conc_, pred_])
         draw_axes = tuple(range(alphas.ndim - 1))
         concentration = np.exp(self.x @ beta_.mean(axis=draw_axes) + alphas.mean(axis=draw_axes))   # :279
@@ -106,7 +113,10 @@ class SimpleModel(dm.CompositionalModel):
         ref = self.reference_cell_type
         cell_types_nb = self.cell_types[:ref] + self.cell_types[ref + 1:]
         one_chain = params["alpha"].ndim == 2
-        with_chain = (lambda a: np.asarray(a)[None]) if one_chain else np.asarray
+        def with_chain(a):
+            if isinstance(a, res.LazyArray):
+                return a.with_leading_axis() if one_chain else a
+            return np.asarray(a)[None] if one_chain else np.asarray(a)
         dims = {"alpha": ["cell_type"], "b": ["covariate", "cell_type_nb"], "beta": ["covariate", "cell_type"],
                 "concentration": ["sample", "cell_type"], "prediction": ["sample", "cell_type"]}
         coords = {"cell_type": res.Coord(self.cell_types), "cell_type_nb": res.Coord(cell_types_nb),

@@ -134,6 +134,7 @@ class CompositionalModel:
         if chains == 1:
             states = [s[0] for s in states]
             kr = {k: v[0] for k, v in kr.items()}
+        self._last_out = (prob, out)                                  # device-resident draws, for the lazy predictive
         self._last_run = {"kernel_ms": out.kernel_ms, "warps_per_chain": out.warps_per_chain, "grid": out.grid,
                           "chains": chains, "launches": out.launches}
         return states, kr, duration
@@ -166,10 +167,44 @@ class CompositionalModel:
             num_results, num_burnin, kernel, init, trace_fn=lambda kr: {new: kr[old] for new, old in trace_keys})
         states_burnin, sample_stats, acc_rate = self.get_chains_after_burnin(states, kernel_results, num_burnin,
                                                                              is_nuts=(method == "nuts"))
-        y_hat = self.get_y_hat(states_burnin, num_results, num_burnin)
+        y_hat = self.get_y_hat(states_burnin, num_results, num_burnin, lazy=True)
+        self._last_out = None                                         # the lazy arrays hold what they need
         sampling_stats = {"chain_length": num_results, "num_burnin": num_burnin, "acc_rate": acc_rate,
                           "duration": duration, "y_hat": y_hat}
         return self.make_result(states_burnin, sample_stats, sampling_stats)
+
+    def _lazy_predictive(self, num_burnin: int, one_chain: bool):
+        """`concentration` and `prediction` per draw (after the second burn-in) as arrays that are generated on the
+        device on first use from the draws of the last `sampling` call (K5, `DeviceProblem.predict`); None when there
+        is no device-resident run to refer to."""
+        last = getattr(self, "_last_out", None)
+        if last is None:
+            return None
+        prob, out = last
+        C, S = int(out.draws.shape[1]), int(out.draws.shape[2])
+        n_draws = S - int(num_burnin)
+        if n_draws <= 0:
+            return None
+        N, K = prob.N, prob.K
+        per_draw = C * N * K * out.draws.element_size()
+        step = max(1, int((1 << 29) // max(per_draw, 1)))             # device buffers of at most ~512 MB per call
+
+        def fetcher(which):
+            def fetch(lo, hi):
+                res_ = np.empty((C, hi - lo, N, K), dtype=np.float64)
+                for s0 in range(lo, hi, step):
+                    s1 = min(hi, s0 + step)
+                    conc, pred = prob.predict(out.draws, num_burnin + s0, num_burnin + s1,
+                                              concentration=which == "concentration", prediction=which == "prediction")
+                    t = conc if which == "concentration" else pred
+                    res_[:, s0 - lo:s1 - lo] = t[0].double().cpu().numpy()
+                return res_[0] if one_chain else res_
+            return fetch
+
+        shape = (n_draws, N, K) if one_chain else (C, n_draws, N, K)
+        axis = 0 if one_chain else 1
+        return (res.LazyArray(shape, np.float64, fetcher("concentration"), axis),
+                res.LazyArray(shape, np.float64, fetcher("prediction"), axis))
 
     def sample_hmc(self, num_results: int = int(20e3), num_burnin: int = int(5e3),
                    num_adapt_steps: Optional[int] = None, num_leapfrog_steps: Optional[int] = 10,
@@ -215,6 +250,8 @@ class CompositionalModel:
         one_chain = params["alpha"].ndim == 2
 
         def with_chain(a):
+            if isinstance(a, res.LazyArray):
+                return a.with_leading_axis() if one_chain else a
             a = np.asarray(a)
             return a[None] if one_chain else a
 
@@ -273,9 +310,13 @@ class scCODAModel(CompositionalModel):
         lp, g = prob.logp_grad(theta[None, None].astype(dtype))
         return float(lp.item()), g.double().cpu().numpy()[0, 0]
 
-    def get_y_hat(self, states_burnin: List[np.ndarray], num_results: int, num_burnin: int) -> np.ndarray:
+    def get_y_hat(self, states_burnin: List[np.ndarray], num_results: int, num_burnin: int, lazy: bool = False
+                  ) -> np.ndarray:
         """Derived quantities per draw — ind, b_raw, beta, concentration, prediction are APPENDED to
-        `states_burnin` — and the posterior-mode count matrix (scCODA_model.py:773-840), vectorised."""
+        `states_burnin` — and the posterior-mode count matrix (scCODA_model.py:773-840), vectorised.
+
+        lazy=True (what the sample_* methods pass): `concentration` and `prediction` [draw, sample, cell_type] are not
+        computed here but appended as `LazyArray`s that the device fills on first use."""
         sigma_d, b_offset, ind_raw, alphas = states_burnin[:4]
         ref = self.reference_cell_type
         s = 50.0 * ind_raw
@@ -284,8 +325,12 @@ class scCODAModel(CompositionalModel):
         b_raw_ = b_offset * sigma_d                                               # :812
         beta_nb = ind_ * b_raw_                                                   # :814
         beta_ = np.insert(beta_nb, ref, 0.0, axis=-1)                             # :816-820
-        conc_ = np.exp(np.einsum("nd,...dk->...nk", self.x, beta_) + alphas[..., None, :])   # :821-822
-        pred_ = self.n_total[:, None] * conc_ / conc_.sum(axis=-1, keepdims=True)             # :824-827 DirMult mean
+        lz = self._lazy_predictive(num_burnin, one_chain=alphas.ndim == 2) if lazy else None
+        if lz is not None and lz[0].shape[:-2] == alphas.shape[:-1]:
+            conc_, pred_ = lz
+        else:
+            conc_ = np.exp(np.einsum("nd,...dk->...nk", self.x, beta_) + alphas[..., None, :])   # :821-822
+            pred_ = self.n_total[:, None] * conc_ / conc_.sum(axis=-1, keepdims=True)          # :824-827 DirMult mean
         states_burnin.extend([ind_, b_raw_, beta_, conc_, pred_])                 # :830-834
         draw_axes = tuple(range(alphas.ndim - 1))
         betas_final = beta_.mean(axis=draw_axes)

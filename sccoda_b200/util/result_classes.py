@@ -36,6 +36,80 @@ class Coord:
         return f"Coord({self.values!r})"
 
 
+class LazyArray:
+    """Read-only array that is computed on first use.
+
+    The posterior-predictive quantities of a run (`concentration`, `prediction`: [draw, sample, cell_type] per chain)
+    are generated on the device from the device-resident draws when somebody looks at them (`sccoda_predict`, K5)
+    instead of being materialised on the host for every run (the reference builds them in per-draw python loops,
+    scCODA_model.py:821-827).  Quacks like a numpy array: `shape`, `dtype`, `ndim`, `len()`, indexing, `np.asarray`,
+    and every other ndarray attribute through the materialised value; `block(lo, hi)` fetches a range of draws
+    without materialising the rest; pickles as the materialised array.
+
+    fetch(lo, hi) -> ndarray with the draws [lo, hi) along `draw_axis`.
+    """
+
+    def __init__(self, shape, dtype, fetch, draw_axis: int = 0):
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(dtype)
+        self._fetch = fetch
+        self._draw_axis = int(draw_axis)
+        self._value = None
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape))
+
+    @property
+    def is_materialized(self):
+        return self._value is not None
+
+    def block(self, lo: int, hi: int) -> np.ndarray:
+        """The draws [lo, hi) only."""
+        if self._value is not None:
+            idx = (slice(None),) * self._draw_axis + (slice(lo, hi),)
+            return self._value[idx]
+        return np.asarray(self._fetch(int(lo), int(hi)))
+
+    def materialize(self) -> np.ndarray:
+        if self._value is None:
+            v = np.asarray(self._fetch(0, self.shape[self._draw_axis]))
+            if v.shape != self.shape:
+                raise ValueError(f"lazy array: fetched shape {v.shape}, expected {self.shape}")
+            self._value = v
+            self._fetch = None                     # drops the reference to the device-resident draws
+        return self._value
+
+    def with_leading_axis(self) -> "LazyArray":
+        return LazyArray((1,) + self.shape, self.dtype, lambda lo, hi: self.block(lo, hi)[None], self._draw_axis + 1)
+
+    def __array__(self, dtype=None, copy=None):
+        v = self.materialize()
+        return v.astype(dtype) if dtype is not None and np.dtype(dtype) != v.dtype else v
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getattr__(self, name):                    # only reached for attributes LazyArray itself does not have
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    def __reduce__(self):
+        return (np.asarray, (self.materialize(),))
+
+    def __repr__(self):
+        state = "materialized" if self._value is not None else "on demand"
+        return f"LazyArray(shape={self.shape}, dtype={self.dtype}, {state})"
+
+
 class Dataset:
     """Dict-backed group: variables are numpy arrays laid out [chain, draw, *dims] (or plain arrays for
     observed data); `ds["name"]`, `ds.name`, `ds.data_vars`, `ds.coords`, `ds.dims`."""

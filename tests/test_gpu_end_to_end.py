@@ -199,3 +199,67 @@ def test_reference_sweep_in_one_launch(data_salm):
     assert res["inclusion_prob"].shape == (8, 8)
     for r in range(8):
         assert res["inclusion_prob"][r, r] == 0.0            # the reference column has no effect
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_predict_kernel_matches_numpy(dtype):
+    """K5 (`sccoda_predict`): concentration / prediction per draw against the host formula of get_y_hat
+    (scCODA_model.py:806-827) on a multi-covariate dataset, full and partial draw ranges."""
+    import torch
+    from conftest import random_states, synthetic_dataset
+    from sccoda_b200.engine import DeviceProblem
+    from sccoda_b200.model.scCODA_model import scCODAModel
+    N, K, D, C, S, ref = 14, 7, 3, 2, 37, 2
+    x, y = synthetic_dataset(5, N=N, K=K, D=D)
+    prob = DeviceProblem.from_arrays(x, y, ref, chains=C, dtype=dtype)
+    th = random_states(np.random.RandomState(1), D, K, C * S).reshape(1, C, S, -1)
+    draws = torch.as_tensor(th.astype(dtype), device=prob.device)
+    model = scCODAModel(reference_cell_type=ref, covariate_matrix=x, data_matrix=y, cell_types=[str(i) for i in range(K)],
+                        covariate_names=[f"x{d}" for d in range(D)], formula="x")
+    thd = draws.double().cpu().numpy()[0]
+    K1 = K - 1
+    states = [thd[..., :D, None], thd[..., D:D + D * K1].reshape(C, S, D, K1),
+              thd[..., D + D * K1:D + 2 * D * K1].reshape(C, S, D, K1), thd[..., -K:]]
+    model.get_y_hat(states, S, 0)
+    conc_ref, pred_ref = states[-2], states[-1]
+    tol = 2e-5 if dtype == np.float32 else 1e-12
+    conc, pred = prob.predict(draws)
+    assert conc.shape == (1, C, S, N, K) and conc.dtype == draws.dtype
+    assert np.allclose(conc[0].double().cpu().numpy(), conc_ref, rtol=tol, atol=0)
+    assert np.allclose(pred[0].double().cpu().numpy(), pred_ref, rtol=tol, atol=0)
+    conc2, none = prob.predict(draws, 5, 19, prediction=False)
+    assert none is None and torch.equal(conc2, conc[:, :, 5:19])
+    none, pred2 = prob.predict(draws, S - 1, S, concentration=False)
+    assert none is None and torch.equal(pred2, pred[:, :, S - 1:])
+    with pytest.raises(RuntimeError):
+        prob.predict(draws, 4, 4)
+
+
+def test_result_predictive_arrays_are_generated_on_demand(tmp_path, data_salm):
+    """`concentration` / `prediction` of a result are LazyArrays filled by the device on first use; values equal the
+    host formula on the stored beta / alpha draws; a saved result holds plain arrays."""
+    import pickle
+    from sccoda_b200.util.result_classes import LazyArray
+    model = mod.CompositionalAnalysis(data_salm, "Condition", reference_cell_type="Goblet")
+    for chains in (1, 3):
+        r = model.sample_hmc(num_results=600, num_burnin=200, verbose=False, seed=5, num_chains=chains)
+        conc, pred = r.posterior["concentration"], r.posterior_predictive["prediction"]
+        assert isinstance(conc, LazyArray) and isinstance(pred, LazyArray) and not conc.is_materialized
+        assert conc.shape == (chains, 400, model.N, model.K) == pred.shape
+        beta, alpha = np.asarray(r.posterior["beta"]), np.asarray(r.posterior["alpha"])
+        ref = np.exp(np.einsum("nd,csdk->csnk", model.x, beta) + alpha[:, :, None, :])
+        blk = conc.block(10, 20)
+        assert blk.shape == (chains, 10, model.N, model.K) and not conc.is_materialized
+        assert np.allclose(blk, ref[:, 10:20], rtol=2e-5)
+        assert np.allclose(np.asarray(conc), ref, rtol=2e-5) and conc.is_materialized
+        assert np.allclose(pred.sum(-1), model.n_total, rtol=1e-5)
+        assert np.allclose(np.asarray(pred), model.n_total[:, None] * ref / ref.sum(-1, keepdims=True), rtol=3e-5)
+        assert np.allclose(r.sampling_stats["y_hat"].sum(1), model.n_total)
+    path = tmp_path / "r.pkl"
+    r2 = model.sample_hmc(num_results=300, num_burnin=100, verbose=False, seed=6)
+    r2.save(str(path))
+    with open(path, "rb") as f:
+        back = pickle.load(f)
+    assert isinstance(back.posterior["concentration"], np.ndarray)
+    assert back.posterior["concentration"].shape == (1, 200, model.N, model.K)
+    assert np.allclose(back.posterior_predictive["prediction"].sum(-1), model.n_total, rtol=1e-5)

@@ -213,3 +213,32 @@ def test_automatic_reference_batch_matches_per_dataset_rule():
     assert [int(r) for r in refs] == [automatic_reference(y[b], 0.2) for b in range(24)]
     with pytest.raises(ValueError, match="large enough presence"):
         automatic_reference_batch(np.zeros((2, 4, 3)))
+
+
+def test_lazy_array_quacks_like_an_array(tmp_path):
+    """`LazyArray` (the on-demand posterior-predictive arrays of a result): nothing is fetched until somebody looks,
+    ranges of draws can be fetched on their own, and the materialised value behaves like / pickles as an ndarray."""
+    import pickle
+    from sccoda_b200.util.result_classes import LazyArray
+    full = np.arange(5 * 3 * 2, dtype=np.float64).reshape(5, 3, 2)
+    calls = []
+
+    def fetch(lo, hi):
+        calls.append((lo, hi))
+        return full[lo:hi]
+
+    a = LazyArray(full.shape, np.float64, fetch)
+    assert a.shape == (5, 3, 2) and a.ndim == 3 and a.size == 30 and len(a) == 5 and a.dtype == np.float64
+    assert not a.is_materialized and calls == [] and "on demand" in repr(a)
+    assert np.array_equal(a.block(1, 3), full[1:3]) and calls == [(1, 3)] and not a.is_materialized
+    b = a.with_leading_axis()
+    assert b.shape == (1, 5, 3, 2) and np.array_equal(b.block(2, 4), full[None, 2:4])
+    assert np.array_equal(np.asarray(a), full) and a.is_materialized and calls[-1] == (0, 5)
+    n_calls = len(calls)
+    assert np.array_equal(a[1:, 0], full[1:, 0]) and a.sum() == full.sum() and np.array_equal(a.mean(axis=0), full.mean(axis=0))
+    assert np.array_equal(a.block(0, 2), full[0:2]) and len(calls) == n_calls          # served from the materialised value
+    assert np.array_equal(np.asarray(b), full[None])
+    back = pickle.loads(pickle.dumps(LazyArray(full.shape, np.float64, fetch)))
+    assert isinstance(back, np.ndarray) and np.array_equal(back, full)
+    with pytest.raises(ValueError):
+        np.asarray(LazyArray((6, 3, 2), np.float64, fetch))                            # fetched shape must match

@@ -13,12 +13,16 @@ import sys
 
 # (file, first line, last line, label) — edit when the sources move
 PHASES = [
-    ("hmc_cc.cuh", 244, 247, "cc: effects"),
-    ("hmc_cc.cuh", 248, 260, "cc: concentrations, totals, pair records"),
-    ("hmc_cc.cuh", 261, 275, "cc: rational + items + odd counts"),
-    ("hmc_cc.cuh", 276, 292, "cc: chain rule"),
-    ("hmc_cc.cuh", 293, 361, "cc: value"),
-    ("hmc_cc.cuh", 362, 600, "cc: sampler (momentum, leapfrog, accept, adapt, trace)"),
+    ("hmc_cc.cuh", 312, 316, "cc: effects"),
+    ("hmc_cc.cuh", 317, 329, "cc: concentrations, totals, pair records"),
+    ("hmc_cc.cuh", 330, 341, "cc: rational + items + odd counts"),
+    ("hmc_cc.cuh", 342, 355, "cc: chain rule"),
+    ("hmc_cc.cuh", 359, 438, "cc: value"),
+    ("hmc_cc.cuh", 443, 510, "cc: kernel prologue"),
+    ("hmc_cc.cuh", 511, 526, "cc: momentum draw + first kick"),
+    ("hmc_cc.cuh", 527, 542, "cc: leapfrog updates"),
+    ("hmc_cc.cuh", 543, 564, "cc: value call + accept"),
+    ("hmc_cc.cuh", 565, 585, "cc: adapt + trace"),
     ("grouped.cuh", 140, 177, "P0 effects (grouped)"),
     ("grouped.cuh", 178, 224, "P1 pair records + totals (grouped)"),
     ("grouped.cuh", 225, 247, "E items (grouped)"),
