@@ -69,6 +69,27 @@ __device__ __forceinline__ void stage_dataset(const KArgs& a, int b, const SmemP
     dt.inreal = (uint32_t)pl.inreal;
     dt.oy = nullptr; dt.opair = nullptr; dt.opos = nullptr; dt.odesc = nullptr;
     dt.NI = 0; dt.NG = 0; dt.NImax = a.NImax; dt.NF = a.NF; dt.tot0 = Umax * K;
+    dt.nrc = (uint32_t)pl.nrc;
+    if (a.grouped && sizeof(T) == 4) {
+        // value pass, row terms in fp32: per-row constants r(n) / lgamma(n) in fp64 here, sum_n lgamma(n) into the
+        // constant (one partial per warp, added in warp order: independent of everything but the block size)
+        T* nrc = sp<T>(dt.nrc);
+        double* red = sp<double>((uint32_t)pl.stage_red);
+        const T* ntot = static_cast<const T*>(a.ntot) + (size_t)b * N;
+        double lg_sum = 0.0;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            const double nn = (double)ntot[n];
+            const double lg = lgamma(nn);
+            nrc[n] = (T)(nn >= 6.0 ? lg - ((nn - 0.5) * log(nn) - nn + 0.91893853320467274178) : lg);
+            lg_sum += lg;
+        }
+        for (int o = 16; o > 0; o >>= 1) lg_sum += __shfl_xor_sync(0xffffffffu, lg_sum, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lg_sum;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        dt.lconst -= tot;
+    }
     if (a.grouped) {
         const int NP = Umax * (K + 1);
         copy_to_smem(sp<T>(dt.pcoef), static_cast<const T*>(a.pcoef) + (size_t)b * NP * 6, NP * 6);

@@ -72,6 +72,7 @@ struct alignas(2 * sizeof(T)) CPsi {
 template <typename T>
 struct DataTile {
     uint32_t ntot;         // smem T[N]
+    uint32_t nrc;          // smem T[N] grouped fp32 build: r(n) (n >= 6) or lgamma(n) of the row totals, cf. eycst
     uint32_t xu;           // smem T[U,D] unique covariate rows
     uint32_t grp;          // smem int[N] group of row n (non-decreasing)
     uint32_t rstart;       // smem int[U+1] first row of each group
@@ -529,8 +530,10 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     }
 #pragma unroll 1
     for (int d = tid; d < D; d += TS) {
-        const double s = (double)sigma[d];
-        if (s >= 0.0) lp -= log1p(s * s);
+        // in the arithmetic type: the fp64 log1p of the fp32 build was 16 % of the NUTS kernel's instructions at
+        // BASELINE config 3, executed by one warp while the others wait at the next barrier
+        const T s = sigma[d];
+        if (s >= T(0)) lp -= (double)t_log1p(s * s);
     }
     // DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c)                               (:746-751)
     // Guard (documented deviation): beyond c_max the lgamma differences have lost all
@@ -559,7 +562,14 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     for (int n = tid; n < dm.N; n += TS) {
         if constexpr (Rec::has_totals) {
             // grouped path: the gradient pass left S_u in the record of the total pair
-            lp += lgamma_rowdiff_f64((double)cp[dt.tot0 + grp[n]].c, (double)ntot[n]);
+            if constexpr (sizeof(T) == 4) {
+                // -[lgamma(S+n) - lgamma(S) - lgamma(n)] in the cancellation-free fp32 forms (as cc_value); the
+                // sum of lgamma(n) was moved into the constant at staging
+                const T S = cp[dt.tot0 + grp[n]].c, nn = ntot[n], rc = sp<T>(dt.nrc)[n];
+                lp -= (double)(S >= T(6) ? lgamma_joint(S, nn, rc) : lgamma_shift(S, nn, rc) - lgamma_pos(S));
+            } else {
+                lp += lgamma_rowdiff_f64((double)cp[dt.tot0 + grp[n]].c, (double)ntot[n]);
+            }
         } else {
             const Rec* cu = cp + grp[n] * K;
             // S in fp32 pairs, combined in fp64 (the conversions are the expensive part of an fp64 accumulation)

@@ -141,6 +141,9 @@ __device__ __forceinline__ float lgamma_joint(float c, float y, float ycst) {
 // Stirling remainder r(y) of a count >= 6 (what _pack.py stores as eycst), on the fly
 __device__ __forceinline__ float stirling_rem_of(float y) { return stirling_rem(rcp_fast(y)); }
 
+__device__ __forceinline__ float t_log1p(float v) { return log1pf(v); }
+__device__ __forceinline__ double t_log1p(double v) { return log1p(v); }
+
 __device__ __forceinline__ float sigmoid_stable(float s) {
     // == exp(s)/(1+exp(s)) (scCODA_model.py:724-725) wherever that is finite; no overflow for large |s|
     const float e = ex2_fast(-fabsf(s) * SCCODA_LOG2EF);
