@@ -747,16 +747,16 @@ __global__ void __launch_bounds__(128, 4) nuts_cc_kernel(const __grid_constant__
                 if (isnan(energy)) energy = -CUDART_INF;
                 const double delta = energy - e0;
                 const bool divergent = !(-delta < 1000.0);
-                const double w_new = logaddexp_d(w_s, delta);
+                const double w_new = nuts_logaddexp<T>(w_s, delta);
                 const double u = (double)rng_uniform<T>(key, leaf_serial++, (uint32_t)t, STREAM_NUTS_LEAF);
                 const double thresh = (w_new > -CUDART_INF) ? delta - w_new : CUDART_NAN;
-                if (log1p(-u) <= thresh) {
+                if (nuts_log1m<T>(u) <= thresh) {
                     cc_st(slots + 32 * S_SQ, q);
                     cc_st(slots + 32 * S_SG, gq);
                     s_lp = lqv; s_en = energy;
                 }
                 w_s = w_new;
-                accept_sum += exp(fmin(delta, 0.0));
+                accept_sum += nuts_exp_neg<T>(delta);
                 if (divergent) not_div = false;
                 alive = (!divergent) && no_uturn;
             }
@@ -770,12 +770,12 @@ __global__ void __launch_bounds__(128, 4) nuts_cc_kernel(const __grid_constant__
             double thresh = tree_w - wsum;
             if (isnan(thresh)) thresh = 0.0;
             const double u = (double)rng_uniform<T>(key, (uint32_t)depth, (uint32_t)t, STREAM_NUTS_TOP);
-            if ((log1p(-u) <= thresh) && alive) {
+            if ((nuts_log1m<T>(u) <= thresh) && alive) {
                 cc_st(slots + 32 * S_CQ, cc_ld(slots + 32 * S_SQ));
                 cc_st(slots + 32 * S_CG, cc_ld(slots + 32 * S_SG));
                 c_lp = s_lp; c_energy = s_en; is_acc = true;
             }
-            wsum = logaddexp_d(wsum, tree_w);
+            wsum = nuts_logaddexp<T>(wsum, tree_w);
             cc_st(slots + 32 * e_q, q);
             cc_st(slots + 32 * e_p, p);
             cc_st(slots + 32 * e_g, gq);

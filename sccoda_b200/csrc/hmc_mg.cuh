@@ -722,16 +722,16 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D == 2 ? 3 : 2)) nuts_mg_ke
                 if (isnan(energy)) energy = -CUDART_INF;
                 const double delta = energy - e0;
                 const bool divergent = !(-delta < 1000.0);
-                const double w_new = logaddexp_d(w_s, delta);
+                const double w_new = nuts_logaddexp<T>(w_s, delta);
                 const double u = (double)rng_uniform<T>(key, leaf_serial++, (uint32_t)t, STREAM_NUTS_LEAF);
                 const double thresh = (w_new > -CUDART_INF) ? delta - w_new : CUDART_NAN;
-                if (log1p(-u) <= thresh) {
+                if (nuts_log1m<T>(u) <= thresh) {
                     mg_st<D>(slot(S_SQ), q);
                     mg_st<D>(slot(S_SG), gq);
                     s_lp = lqv; s_en = energy;
                 }
                 w_s = w_new;
-                accept_sum += exp(fmin(delta, 0.0));
+                accept_sum += nuts_exp_neg<T>(delta);
                 if (divergent) not_div = false;
                 alive = (!divergent) && no_uturn;
             }
@@ -745,12 +745,12 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D == 2 ? 3 : 2)) nuts_mg_ke
             double thresh = tree_w - wsum;
             if (isnan(thresh)) thresh = 0.0;
             const double u = (double)rng_uniform<T>(key, (uint32_t)depth, (uint32_t)t, STREAM_NUTS_TOP);
-            if ((log1p(-u) <= thresh) && alive) {
+            if ((nuts_log1m<T>(u) <= thresh) && alive) {
                 mg_st<D>(slot(S_CQ), mg_ld<D>(slot(S_SQ)));
                 mg_st<D>(slot(S_CG), mg_ld<D>(slot(S_SG)));
                 c_lp = s_lp; c_energy = s_en; is_acc = true;
             }
-            wsum = logaddexp_d(wsum, tree_w);
+            wsum = nuts_logaddexp<T>(wsum, tree_w);
             mg_st<D>(slot(e_q), q);
             mg_st<D>(slot(e_p), p);
             mg_st<D>(slot(e_g), gq);

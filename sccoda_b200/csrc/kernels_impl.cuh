@@ -407,6 +407,29 @@ __device__ __forceinline__ double logaddexp_d(double x, double y) {
     const double m = fmax(x, y);
     return m + log(exp(x - m) + exp(y - m));
 }
+// The scalar bookkeeping of a NUTS leaf (subtree weight, multinomial acceptance, accept statistic) in the arithmetic
+// type: the fp32 build evaluates the transcendental functions in fp32 (the values stay doubles; the fp64 versions
+// were ~300 instructions per leaf, executed by every warp of the chain), the fp64 build is unchanged.
+template <typename T>
+__device__ __forceinline__ double nuts_logaddexp(double x, double y) {
+    if constexpr (sizeof(T) == 8) {
+        return logaddexp_d(x, y);
+    } else {
+        if (x == -CUDART_INF) return y;
+        if (y == -CUDART_INF) return x;
+        return fmax(x, y) + (double)log1pf(expf(-fabsf((float)(x - y))));
+    }
+}
+template <typename T>
+__device__ __forceinline__ double nuts_log1m(double u) {   // log(1 - u), u a 24-bit uniform (exact in fp32)
+    if constexpr (sizeof(T) == 8) return log1p(-u);
+    else return (double)log1pf(-(float)u);
+}
+template <typename T>
+__device__ __forceinline__ double nuts_exp_neg(double d) {  // exp(min(d, 0))
+    if constexpr (sizeof(T) == 8) return exp(fmin(d, 0.0));
+    else return (double)expf(fminf((float)d, 0.0f));
+}
 
 template <typename T, int W, bool GR>
 __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
@@ -540,16 +563,16 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
                 if (isnan(energy)) energy = -CUDART_INF;
                 const double delta = energy - e0;
                 const bool divergent = !(-delta < 1000.0);
-                const double w_new = logaddexp_d(w_s, delta);
+                const double w_new = nuts_logaddexp<T>(w_s, delta);
                 const double u = (double)rng_uniform<T>(key, leaf_serial++, (uint32_t)t, STREAM_NUTS_LEAF);
                 const double thresh = (w_new > -CUDART_INF) ? delta - w_new : CUDART_NAN;
-                if (log1p(-u) <= thresh) {
+                if (nuts_log1m<T>(u) <= thresh) {
 #pragma unroll 1
                     for (int i = tid; i < P; i += TS) { sq[i] = q[i]; sg[i] = gq[i]; }
                     s_lp = lqv; s_en = energy;
                 }
                 w_s = w_new;
-                accept_sum += exp(fmin(delta, 0.0));
+                accept_sum += nuts_exp_neg<T>(delta);
                 if (divergent) not_div = false;
                 alive = (!divergent) && no_uturn;
             }
@@ -564,12 +587,12 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
             double thresh = tree_w - wsum;
             if (isnan(thresh)) thresh = 0.0;
             const double u = (double)rng_uniform<T>(key, (uint32_t)depth, (uint32_t)t, STREAM_NUTS_TOP);
-            if ((log1p(-u) <= thresh) && alive) {
+            if ((nuts_log1m<T>(u) <= thresh) && alive) {
 #pragma unroll 1
                 for (int i = tid; i < P; i += TS) { cq[i] = sq[i]; cg[i] = sg[i]; }
                 c_lp = s_lp; c_energy = s_en; is_acc = true;
             }
-            wsum = logaddexp_d(wsum, tree_w);
+            wsum = nuts_logaddexp<T>(wsum, tree_w);
             T d1 = T(0), d2 = T(0);
 #pragma unroll 1
             for (int i = tid; i < P; i += TS) {
