@@ -345,6 +345,14 @@ def test_multi_group_kernel_ragged_batch_and_cell_type_range():
     assert sorted(pk.U.tolist()) == [1, 2, 3, 4] and pk.NOT >= 1
 
 
+@pytest.mark.parametrize("K,N,kind", [(2, 64, "factorial2x2x2"), (3, 90, "levels3"), (12, 120, "conditions4")])
+def test_multi_group_kernel_long_groups_and_few_cell_types(K, N, kind):
+    """Several items per pair (groups of 8 to 30 rows) and the smallest cell-type counts on the multi-group kernel."""
+    xs, ys = zip(*[_multi_group_dataset(130 + b, kind, N=N, K=K) for b in range(2)])
+    outs, pk, _, _ = _mg_vs_generic(xs, ys, [K - 1, 0], steps=8)
+    assert pk.NT >= 2
+
+
 def test_multi_group_kernel_frozen_spike_slab():
     """SimpleModel semantics (sigma_d and ind_raw frozen) on the multi-group kernel."""
     from sccoda_b200._pack import pack
