@@ -30,12 +30,14 @@ __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
 }
 __device__ __forceinline__ f32x2 dup2(float v) { return pk2(v, v); }
 __device__ __forceinline__ float lo2(f32x2 v) {
-    float lo, hi;
+    float lo;
+    float hi __attribute__((unused));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
     return lo;
 }
 __device__ __forceinline__ float hi2(f32x2 v) {
-    float lo, hi;
+    float lo __attribute__((unused));
+    float hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
     return hi;
 }

@@ -461,7 +461,7 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
     T* gq = vec + 14 * vs;
     T* ck_p = vec + 15 * vs;
     T* ck_rho = vec + (15 + (maxd + 1)) * vs;
-    const uint32_t o_q = cs.vec + 12 * vsb, o_gq = cs.vec + 14 * vsb;
+    const uint32_t o_q = cs.vec + 12 * vsb;
     const size_t chain = (size_t)b * a.C + c;
     const RngKey key{(uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), a.chain_id0 + (uint32_t)chain};
 
