@@ -1,5 +1,5 @@
 // K2mg — HMC on the lane-per-cell-type layout of hmc_cc.cuh for designs with MORE than two covariate groups:
-// up to 8 groups (distinct rows of the design matrix: four conditions, a 2x2 or 2x2x2 factorial ...), D <= 3
+// up to 16 groups (distinct rows of the design matrix: a few conditions, 2x2 ... 2x2x2x2 factorials), D <= 4
 // covariates, K <= 31 cell types, fp32, one warp per chain.
 //
 // Same algorithm, Philox streams and per-parameter arithmetic as hmc_kernel (kernels_impl.cuh; reference:
@@ -359,7 +359,7 @@ static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off,
 // Kernel
 // ------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : 4)) hmc_mg_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : (D == 3 ? 4 : 3))) hmc_mg_kernel(const __grid_constant__ KArgs a) {
     using T = float;
     const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
     const int cpc = blockDim.x >> 5;
@@ -568,7 +568,7 @@ __device__ __forceinline__ float mg_dot(const MgVec<D>& x, const MgVec<D>& y, in
     return lane == 0 ? v + sv : v;
 }
 template <int D>
-__global__ void __launch_bounds__(128, D == 1 ? 4 : (D == 2 ? 3 : 2)) nuts_mg_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_kernel(const __grid_constant__ KArgs a) {
     using T = float;
     using V = MgVec<D>;
     const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;

@@ -10,7 +10,7 @@ namespace sccoda {
 enum {
     KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2,
     KIND_HMC_CC = 3, KIND_NUTS_CC = 4,   // case/control specialisations (hmc_cc.cuh)
-    KIND_HMC_MG = 5, KIND_NUTS_MG = 6    // up to 8 covariate groups, D <= 3 on the same lane-per-cell-type layout (hmc_mg.cuh)
+    KIND_HMC_MG = 5, KIND_NUTS_MG = 6    // up to 16 covariate groups, D <= 4 on the same lane-per-cell-type layout (hmc_mg.cuh)
 };
 
 }  // namespace sccoda
@@ -142,7 +142,7 @@ struct MgPlan {
     size_t cf, yv, ov, rows, el, xg, cnt, bounds, red, data_total;   // per CTA
     size_t pc, vec, slots, chain_total;                               // per chain (relative)
 };
-constexpr int kMgMaxGroups = 8, kMgMaxD = 3;
+constexpr int kMgMaxGroups = 16, kMgMaxD = 4;
 // n_slots: stored vectors of the NUTS tree (D float4 per lane each; 0 for HMC)
 __host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NT, int NOT, int n_slots) {
     MgPlan p;

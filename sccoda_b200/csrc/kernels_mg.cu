@@ -14,6 +14,7 @@ cudaError_t launch_hmc_mg(const KArgs& a, int grid, int block, size_t smem, cuda
         case 1: return launch_hmc_mg_d<1>(a, grid, block, smem, st);
         case 2: return launch_hmc_mg_d<2>(a, grid, block, smem, st);
         case 3: return launch_hmc_mg_d<3>(a, grid, block, smem, st);
+        case 4: return launch_hmc_mg_d<4>(a, grid, block, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -29,6 +30,7 @@ cudaError_t launch_nuts_mg(const KArgs& a, int grid, int block, size_t smem, cud
         case 1: return launch_nuts_mg_d<1>(a, grid, block, smem, st);
         case 2: return launch_nuts_mg_d<2>(a, grid, block, smem, st);
         case 3: return launch_nuts_mg_d<3>(a, grid, block, smem, st);
+        case 4: return launch_nuts_mg_d<4>(a, grid, block, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -256,6 +256,12 @@ def _design(kind, N, rs):
     if kind == "factorial2x2x2":               # D = 3, 8 groups
         x = ((np.arange(N)[:, None] >> np.arange(3)[None, :]) & 1).astype(float)
         return x[rs.permutation(N)]
+    if kind == "conditions5":                  # D = 4, 5 groups
+        lv = np.arange(N) % 5
+        return (lv[:, None] == np.arange(1, 5)[None, :]).astype(float)
+    if kind == "factorial2x2x2x2":             # D = 4, 16 groups
+        x = ((np.arange(N)[:, None] >> np.arange(4)[None, :]) & 1).astype(float)
+        return x[rs.permutation(N)]
     if kind == "groups3_d2":                   # D = 2, 3 groups (odd group count: one empty slot in the last pair)
         lv = np.arange(N) % 3
         return np.stack([lv == 1, lv == 2], axis=1).astype(float)
@@ -312,14 +318,15 @@ def _mg_vs_generic(xs, ys, refs, method=0, C=2, steps=12, seed=4):
 
 
 @pytest.mark.parametrize("method", [0, 1])
-@pytest.mark.parametrize("kind", ["levels3", "factorial2x2", "conditions4", "factorial2x2x2", "groups3_d2"])
+@pytest.mark.parametrize("kind", ["levels3", "factorial2x2", "conditions4", "factorial2x2x2", "groups3_d2", "conditions5",
+                                  "factorial2x2x2x2"])
 def test_multi_group_kernel_follows_generic_kernel(kind, method):
-    """The lane-per-cell-type kernel for up to 8 covariate groups and D <= 3 (hmc_mg.cuh) against the generic kernel and
-    the oracle's log-density, on designs with 3, 4 and 8 groups."""
+    """The lane-per-cell-type kernel for up to 16 covariate groups and D <= 4 (hmc_mg.cuh) against the generic kernel and
+    the oracle's log-density, on designs with 3 to 16 groups."""
     K = 9
-    xs, ys = zip(*[_multi_group_dataset(80 + b, kind, N=24, K=K, zero_frac=0.1 * (b == 1)) for b in range(3)])
+    xs, ys = zip(*[_multi_group_dataset(80 + b, kind, N=32, K=K, zero_frac=0.1 * (b == 1)) for b in range(3)])
     outs, pk, prob, init = _mg_vs_generic(xs, ys, [K - 1, 0, 4], method=method)
-    assert 2 < pk.Umax <= 8
+    assert 2 < pk.Umax <= 16
     # chunked resume is bit-identical to the single launch
     smp = prob.make_sampler(method, 12, 0, num_adapt=12, seed=4, warps_per_chain=1)
     many = prob.sample(init, smp, chunk=5)
@@ -423,15 +430,15 @@ def test_case_control_nuts_kernel_follows_generic_kernel():
     assert np.array_equal(many.stats.cpu().numpy(), outs[1].stats.cpu().numpy(), equal_nan=True)
 
 
-@pytest.mark.parametrize("kind", ["levels3", "factorial2x2", "conditions4", "factorial2x2x2"])
+@pytest.mark.parametrize("kind", ["levels3", "factorial2x2", "conditions4", "factorial2x2x2", "factorial2x2x2x2"])
 def test_multi_group_nuts_kernel_follows_generic_kernel(kind):
-    """The lane-per-cell-type NUTS kernel for up to 8 covariate groups / D <= 3 builds the same trees as the generic NUTS
+    """The lane-per-cell-type NUTS kernel for up to 16 covariate groups / D <= 4 builds the same trees as the generic NUTS
     kernel for the first transitions (same Philox streams, same tree logic), and its traced log-density is the oracle's."""
     from oracle import np_oracle as o
     from sccoda_b200._pack import pack
     from sccoda_b200.engine import DeviceProblem
     B, C, K = 2, 3, 9
-    xs, ys = zip(*[_multi_group_dataset(110 + b, kind, N=24, K=K, zero_frac=0.1 * (b == 1)) for b in range(B)])
+    xs, ys = zip(*[_multi_group_dataset(110 + b, kind, N=32, K=K, zero_frac=0.1 * (b == 1)) for b in range(B)])
     D = xs[0].shape[1]
     refs = [K - 1, 3]
     init = _init(np.random.RandomState(12), D, K, B * C).reshape(B, C, -1) * 0.5

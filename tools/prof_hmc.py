@@ -29,9 +29,15 @@ ap.add_argument("--step-size", type=float, default=0.02)
 ap.add_argument("--generic", type=int, default=0, help="1: never take the case/control kernel")
 ap.add_argument("--grouped", type=int, default=-1, help="-1 auto, 0 element path, 1 pair/item path")
 ap.add_argument("--conditions", type=int, default=2, help="> 2: one-hot coded conditions (D = conditions - 1), n-per-group rows each")
+ap.add_argument("--factorial", type=int, default=0, help="F > 0: F binary covariates (D = F), 2^F groups of n-per-group rows")
 a = ap.parse_args()
 
-if a.conditions > 2:
+if a.factorial > 0:
+    G = 1 << a.factorial
+    x, y, _ = generate_sweep(a.datasets, K=a.K, n_per_group=G * a.n_per_group // 2)
+    lv = np.arange(y.shape[1]) % G
+    x = np.broadcast_to(((lv[:, None] >> np.arange(a.factorial)[None, :]) & 1).astype(float), (a.datasets, y.shape[1], a.factorial)).copy()
+elif a.conditions > 2:
     x, y, _ = generate_sweep(a.datasets, K=a.K, n_per_group=a.conditions * a.n_per_group // 2)
     lv = np.arange(y.shape[1]) % a.conditions
     x = np.broadcast_to((lv[:, None] == np.arange(1, a.conditions)[None, :]).astype(float), (a.datasets, y.shape[1], a.conditions - 1)).copy()
