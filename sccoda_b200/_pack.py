@@ -187,8 +187,9 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
     """x: [B,N,D] or [N,D]; y: [B,N,K] or [N,K]; ref: int or [B].
 
     grouped: None = choose (pair/item gradient path for designs with at most 16 covariate groups, D <= 4 and K <= 31,
-    and whenever the covariate groups are large enough that the item padding stays below 60 % of the counts),
-    True / False = force."""
+    and whenever the covariate groups are large enough that the item padding stays below 60 % of the counts — unless
+    the pair/item arrays of the dataset would not fit one CTA's shared memory), True / False = force."""
+    args_in, auto = (x, y, ref), grouped is None
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
     if y.ndim == 2:
@@ -269,7 +270,7 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
         order = np.argsort(ey < 6.0, axis=1, kind="stable")
         ey, eycst, eidx = (np.take_along_axis(a, order, axis=1) for a in (ey, eycst, eidx))
         nbig = (ey >= 6.0).sum(axis=1).astype(np.int32)
-    return PackedProblem(grouped=int(bool(grouped)), NImax=it["NImax"], NOmax=it["NOmax"], NGmax=it["NGmax"],
+    pk = PackedProblem(grouped=int(bool(grouped)), NImax=it["NImax"], NOmax=it["NOmax"], NGmax=it["NGmax"],
                          NF=it["NF"], NT=it["NT"], NOT=it["NOT"], NI=it["NI"], NG=it["NG"], iy=np.ascontiguousarray(it["iy"], dtype),
                          ipair=it["ipair"], ipos=it["ipos"], inreal=it["inreal"], pcoef=np.ascontiguousarray(it["pcoef"], dtype),
                          oy=np.ascontiguousarray(it["oy"], dtype), opair=it["opair"], opos=it["opos"],
@@ -283,3 +284,25 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
                          grp=np.ascontiguousarray(grp), rstart=np.ascontiguousarray(rstart), U=U, ref=ref,
                          lconst=np.ascontiguousarray(lconst, np.float64),
                          row_order=np.stack(orders), logp_const=logp_const)
+    if auto and pk.grouped and not _grouped_layout_fits(pk):
+        return pack(*args_in, dtype=dtype, pseudocount=pseudocount, grouped=False)
+    return pk
+
+
+def _grouped_layout_fits(pk: PackedProblem) -> bool:
+    """Can the kernels hold the pair/item layout of this problem in one CTA's shared memory?  Asked of the library's
+    own launch planner (`sccoda_launch_plan`, NUTS with the default tree depth = the largest footprint); very long
+    datasets (thousands of rows) fall back to the element layout, whose list streams from global memory."""
+    import ctypes
+    try:
+        from . import _native as nat
+        lib = nat.lib()
+    except (OSError, RuntimeError):
+        return True                                  # no library here: sampling will complain loudly, not the packer
+    prob = nat.Problem(C=1, **nat.problem_fields(pk, lambda name: getattr(pk, name).ctypes.data))
+    smp = nat.Sampler(method=nat.METHOD_NUTS, num_results=1, num_burnin=0, num_adapt=0, num_leapfrog=10, max_tree_depth=10,
+                      step_begin=0, step_end=0, step_size=0.01, target_accept=0.75, seed=0, chain_id0=0,
+                      warps_per_chain=0, store_draws=1, chains_per_cta=0, generic_only=0, freeze_spike_slab=0)
+    out = [ctypes.c_int32() for _ in range(4)]
+    rc = lib.sccoda_launch_plan(ctypes.byref(prob), ctypes.byref(smp), *(ctypes.byref(v) for v in out))
+    return rc != -9

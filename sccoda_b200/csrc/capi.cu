@@ -98,40 +98,51 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, i
         max_smem = 227 * 1024;  // B200; used only for planning without a device
     }
     const int NK = p->N * p->K;
-    int W = W_req;
-    if (W == 0 && sccoda::select_kind(a, kind, p->dtype, 1) != kind && (p->NT <= 8 || p->B * p->C >= 148 * 8)) {
-        // case/control shape: the lane-per-cell-type kernel (one warp per chain) unless a few chains face very long
-        // groups (more than 40 rows per group: the items of a pair are walked by one lane)
-        W = 1;
+    const int kind_in = kind;
+    // Two attempts: the lane-per-cell-type kernels where the shape allows them, then the generic kernels (a dataset
+    // whose staged tile does not fit one CTA's shared memory in the specialised layout still runs)
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        kind = kind_in;
+        if (attempt == 1) a.generic_only = 1;
+        int W = W_req;
+        if (W == 0 && sccoda::select_kind(a, kind, p->dtype, 1) != kind && (p->NT <= 8 || p->B * p->C >= 148 * 8)) {
+            // case/control and multi-group shapes: the lane-per-cell-type kernels (one warp per chain) unless a few
+            // chains face very long groups (more than 40 rows per group: the items of a pair are walked by one lane)
+            W = 1;
+        }
+        if (W == 0) {
+            const int n_chains = p->B * p->C;
+            const int w_work = pow2_ceil((NK + 511) / 512);
+            const int fill = (148 * 8) / n_chains;  // warps per chain that would give ~8 warps per SM
+            const int w_fill = pow2_floor(fill > 0 ? fill : 1);
+            const int w_cap = pow2_ceil((NK + 31) / 32);  // never fewer than one element per thread
+            const int w_lim = w_fill < w_cap ? w_fill : w_cap;
+            W = w_work > w_lim ? w_work : w_lim;
+            if (W > 16) W = 16;
+            if (W < 1) W = 1;
+        }
+        if (W != 1 && W != 2 && W != 4 && W != 8 && W != 16) return fail(-8, "warps_per_chain must be 0,1,2,4,8,16");
+        kind = sccoda::select_kind(a, kind, p->dtype, W);   // specialised kernels (may need less shared memory)
+        const bool specialised = kind != kind_in;
+        int cpc = cpc_req > 0 ? cpc_req : 128 / (32 * W);
+        const int cpc_cap = (W <= 4 ? 128 : 32 * W) / (32 * W);   // launch bounds of the kernels
+        if (cpc > cpc_cap) cpc = cpc_cap;
+        if (cpc < 1) cpc = 1;
+        if (cpc > p->C) cpc = p->C;
+        // element list in shared memory: fp32 build only, and only while one chain group still fits
+        a.el_smem = (p->dtype == SCCODA_F32) ? 1 : 0;
+        if (a.el_smem && (int)sccoda::smem_bytes_for(a, kind, W, 1, p->dtype) > max_smem) a.el_smem = 0;
+        while (cpc > 1 && (int)sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype) > max_smem) cpc -= 1;
+        const size_t smem = sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype);
+        if ((int)smem > max_smem) {
+            if (specialised && attempt == 0 && !a.generic_only) continue;
+            return fail(-9, "problem needs %zu bytes of shared memory per chain group, device limit is %d", smem, max_smem);
+        }
+        out->W = W; out->cpc = cpc; out->smem = (int)smem;
+        out->grid = p->B * ((p->C + cpc - 1) / cpc);
+        return 0;
     }
-    if (W == 0) {
-        const int n_chains = p->B * p->C;
-        const int w_work = pow2_ceil((NK + 511) / 512);
-        const int fill = (148 * 8) / n_chains;  // warps per chain that would give ~8 warps per SM
-        const int w_fill = pow2_floor(fill > 0 ? fill : 1);
-        const int w_cap = pow2_ceil((NK + 31) / 32);  // never fewer than one element per thread
-        const int w_lim = w_fill < w_cap ? w_fill : w_cap;
-        W = w_work > w_lim ? w_work : w_lim;
-        if (W > 16) W = 16;
-        if (W < 1) W = 1;
-    }
-    if (W != 1 && W != 2 && W != 4 && W != 8 && W != 16) return fail(-8, "warps_per_chain must be 0,1,2,4,8,16");
-    kind = sccoda::select_kind(a, kind, p->dtype, W);   // specialised kernels (may need less shared memory)
-    int cpc = cpc_req > 0 ? cpc_req : 128 / (32 * W);
-    const int cpc_cap = (W <= 4 ? 128 : 32 * W) / (32 * W);   // launch bounds of the kernels
-    if (cpc > cpc_cap) cpc = cpc_cap;
-    if (cpc < 1) cpc = 1;
-    if (cpc > p->C) cpc = p->C;
-    // element list in shared memory: fp32 build only, and only while one chain group still fits
-    a.el_smem = (p->dtype == SCCODA_F32) ? 1 : 0;
-    if (a.el_smem && (int)sccoda::smem_bytes_for(a, kind, W, 1, p->dtype) > max_smem) a.el_smem = 0;
-    while (cpc > 1 && (int)sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype) > max_smem) cpc -= 1;
-    const size_t smem = sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype);
-    if ((int)smem > max_smem)
-        return fail(-9, "problem needs %zu bytes of shared memory per chain group, device limit is %d", smem, max_smem);
-    out->W = W; out->cpc = cpc; out->smem = (int)smem;
-    out->grid = p->B * ((p->C + cpc - 1) / cpc);
-    return 0;
+    return fail(-9, "problem does not fit the shared memory of one CTA");
 }
 
 int fill_sampler(const sccoda_sampler* s, sccoda::KArgs& a, int* kind) {

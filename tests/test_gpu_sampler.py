@@ -360,6 +360,31 @@ def test_multi_group_kernel_long_groups_and_few_cell_types(K, N, kind):
     assert pk.NT >= 2
 
 
+@pytest.mark.parametrize("N,grouped_expected", [(1000, 1), (2000, 0)])
+def test_long_case_control_dataset_runs_on_the_generic_kernels(N, grouped_expected):
+    """Datasets too long for the lane-per-cell-type tile (N = 1000) or for the pair/item layout altogether (N = 2000)
+    still run — on the generic kernels — and trace the oracle's log-density."""
+    from oracle import np_oracle as o
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    K, C, steps = 20, 2, 4
+    x, y = synthetic_dataset(7, N=N, K=K)
+    pk = pack(x, y, K - 1, dtype=np.float32)
+    assert pk.grouped == grouped_expected
+    prob = DeviceProblem(pk, chains=C)
+    init = _init(np.random.RandomState(1), 1, K, C).reshape(1, C, -1) * 0.3
+    init[..., 0] = 1.0
+    out = prob.sample(init, prob.make_sampler(0, steps, 0, num_adapt=steps, seed=2, step_size=0.002))
+    assert out.kernel_kind == 1
+    d = out.draws.double().cpu().numpy()
+    lp = out.stat("target_log_prob").double().cpu().numpy()
+    assert np.isfinite(d).all() and np.isfinite(lp).all()
+    m = o.prepare(x, y, K - 1)
+    for c in range(C):
+        ref = np.array([o.logp(d[0, c, i], m) for i in range(steps)])
+        assert np.abs(lp[0, c] - ref).max() < 5e-6 * np.abs(ref).max() + 4e-3, np.abs(lp[0, c] - ref).max()
+
+
 def test_multi_group_kernel_frozen_spike_slab():
     """SimpleModel semantics (sigma_d and ind_raw frozen) on the multi-group kernel."""
     from sccoda_b200._pack import pack

@@ -89,6 +89,34 @@ def test_launch_plan_scales_warps_for_few_chains_and_big_models():
     assert rc == 0 and w == 2
 
 
+def test_launch_plan_falls_back_when_the_specialised_tile_does_not_fit():
+    """Long case/control datasets: the lane-per-cell-type kernels stage the whole element list (16 B per count) in
+    shared memory; when that does not fit, the planner takes the generic kernels instead of failing, and the packer
+    leaves the pair/item layout when even those cannot hold it."""
+    kind = ctypes.c_int32()
+    x, y = synthetic_dataset(0, N=200, K=20)
+    pk = pack(x, y, 19)
+    assert pk.grouped == 1
+    assert nat.lib().sccoda_kernel_kind(ctypes.byref(_problem(pk, 4096)), ctypes.byref(_sampler()), ctypes.byref(kind)) == 0
+    assert kind.value == 3
+    x, y = synthetic_dataset(0, N=1000, K=20)
+    pk = pack(x, y, 19)
+    assert pk.grouped == 1
+    for method, generic_kind in ((0, 1), (2, 2)):
+        rc, w, cpc, grid, smem = _plan(_problem(pk, 4096), _sampler(method=method))
+        assert rc == 0 and w > 1 and smem <= 227 * 1024
+        assert nat.lib().sccoda_kernel_kind(ctypes.byref(_problem(pk, 4096)), ctypes.byref(_sampler(method=method)),
+                                            ctypes.byref(kind)) == 0
+        assert kind.value == generic_kind
+    x, y = synthetic_dataset(0, N=2000, K=20)
+    assert pack(x, y, 19, grouped=True).grouped == 1
+    assert _plan(_problem(pack(x, y, 19, grouped=True), 4), _sampler(method=2))[0] == -9
+    pk = pack(x, y, 19)                                  # automatic choice: element layout
+    assert pk.grouped == 0
+    rc, w, cpc, grid, smem = _plan(_problem(pk, 4), _sampler(method=2))
+    assert rc == 0 and smem <= 227 * 1024
+
+
 @pytest.mark.parametrize("kw,code", [(dict(method=7), -11), (dict(num_results=0), -12), (dict(num_leapfrog=0), -13),
                                       (dict(method=2, max_tree_depth=0), -14), (dict(step_size=0.0), -15),
                                       (dict(step_begin=10, step_end=5), -16), (dict(warps_per_chain=3), -8)])
