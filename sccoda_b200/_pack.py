@@ -183,6 +183,15 @@ def build_items(ys: np.ndarray, ntot: np.ndarray, rstart: np.ndarray, U: np.ndar
                 oy=oy, opair=opair, opos=opos, odesc=odesc, inreal=inreal)
 
 
+def _no_items(B: int, K: int, Umax: int) -> dict:
+    """Placeholder pair/item arrays for a problem that only has the element layout."""
+    NP = Umax * (K + 1)
+    return dict(NT=1, NOT=0, NF=2, NImax=2, NOmax=1, NGmax=1, NI=np.zeros(B, np.int32), NG=np.zeros(B, np.int32),
+                iy=np.full((B, ITEM_R, 2), 6.0), ipair=np.zeros((B, 2), np.uint16), ipos=np.zeros((B, 2), np.uint16),
+                pcoef=np.zeros((B, NP, 6)), oy=np.ones((B, 1)), opair=np.zeros((B, 1), np.uint16),
+                opos=np.zeros((B, 1), np.uint16), odesc=np.zeros((B, 1), np.uint32), inreal=np.zeros((B, 2), np.uint8))
+
+
 def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) -> PackedProblem:
     """x: [B,N,D] or [N,D]; y: [B,N,K] or [N,K]; ref: int or [B].
 
@@ -257,7 +266,14 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
     eycst = ycst[bidx, rows, perm].reshape(B, N * K)
     uk = grp[:, None, :].astype(np.int64) * K + perm                          # [B,K,N]
     eidx = (uk | (rows.astype(np.int64) << 16)).astype(np.uint32).reshape(B, N * K)
-    it = build_items(ys, ntot, rstart, U, Umax)
+    try:
+        it = build_items(ys, ntot, rstart, U, Umax)
+    except ValueError:
+        if grouped:
+            raise
+        # too many pairs / items for the 16-bit indices of the pair/item layout: element layout, empty item arrays
+        it = _no_items(B, K, Umax)
+        grouped = False
     if grouped is None:
         # designs with few covariate groups (case/control, a handful of conditions, small factorials) always take the
         # pair/item layout: the lane-per-cell-type kernels (hmc_cc.cuh, hmc_mg.cuh) evaluate a padded item as cheaply

@@ -168,3 +168,16 @@ def test_pair_item_layout_auto_mode():
     b = int(np.argmin(pk.NI))
     assert np.all(pk.iy[b, :, pk.NI[b]:] == 6.0) and np.all(pk.ipair[b, pk.NI[b]:] == 0)
     assert np.all(pk.ipos[b, pk.NI[b]:] == pk.NP * pk.NF)            # padding items write to the spare slot
+
+
+def test_auto_layout_never_raises_for_oversized_item_tables():
+    """A continuous design with many rows and cell types overflows the 16-bit indices of the pair/item layout: forcing
+    that layout raises, the automatic choice silently takes the element layout."""
+    rs = np.random.RandomState(1)
+    N, K, D = 600, 80, 6
+    x = rs.randn(N, D)
+    y = rs.poisson(50, size=(N, K)).astype(float) + 1
+    with pytest.raises(ValueError):
+        pack(x, y, 3, grouped=True)
+    pk = pack(x, y, 3)
+    assert pk.grouped == 0 and pk.Umax == N and int(pk.NI.sum()) == 0
