@@ -573,3 +573,50 @@ def test_diverging_flag_and_negative_sigma_rejection():
     assert np.array_equal(div == 1, lar < -1000)                          # scCODA_model.py:299
     acc = out.stat("is_accepted").cpu().numpy()
     assert acc[lar == -np.inf].sum() == 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_trace_the_oracle_log_density(seed):
+    """Randomised shapes across the dispatch table (case/control, multi-group and generic kernels; HMC, HMC-DA and NUTS;
+    binary, one-hot, continuous and constant designs; counts from sparse to large): whatever kernel the planner picks,
+    the traced log-density is the oracle's log-density at the traced state."""
+    from oracle import np_oracle as o
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    rs = np.random.RandomState(1000 + seed)
+    seen = set()
+    for trial in range(5):
+        N = int(rs.choice([3, 6, 12, 25, 60]))
+        K = int(rs.choice([2, 3, 5, 8, 20, 31, 32, 40]))
+        D = int(rs.choice([1, 2, 3, 4, 5]))
+        mode = int(rs.randint(4))
+        if mode == 0:
+            x = rs.randint(0, 2, size=(N, D)).astype(float)
+        elif mode == 1:
+            x = rs.randn(N, D)
+        elif mode == 2:
+            x = (rs.randint(0, D + 1, size=N)[:, None] == np.arange(1, D + 1)[None, :]).astype(float)
+        else:
+            x = np.zeros((N, D))
+            x[N // 2:, 0] = 1.0
+        y = rs.poisson(rs.choice([0.7, 4.0, 30.0, 400.0]), size=(N, K)).astype(float)
+        y[0, 0] += 1.0
+        ref = int(rs.randint(K))
+        C, steps = 2, 5
+        method = int(rs.randint(3))
+        pk = pack(x, y, ref, dtype=np.float32)
+        prob = DeviceProblem(pk, chains=C)
+        init = _init(rs, D, K, C).reshape(1, C, -1) * 0.3
+        init[..., :D] = 1.0
+        out = prob.sample(init, prob.make_sampler(method, steps, 0, num_adapt=steps, seed=seed, step_size=0.005,
+                                                  max_tree_depth=4))
+        seen.add(out.kernel_kind)
+        d = out.draws.double().cpu().numpy()
+        lp = out.stat("target_log_prob").double().cpu().numpy()
+        assert np.isfinite(d).all() and np.isfinite(lp).all(), (N, K, D, mode, method, out.kernel_kind)
+        m = o.prepare(x, y, ref)
+        for c in range(C):
+            want = np.array([o.logp(d[0, c, i], m) for i in range(steps)])
+            err = np.abs(lp[0, c] - want).max()
+            assert err < 5e-6 * np.abs(want).max() + 4e-3, (N, K, D, mode, method, out.kernel_kind, err)
+    assert len(seen) >= 2
