@@ -1,6 +1,7 @@
 // K2mg — HMC on the lane-per-cell-type layout of hmc_cc.cuh for designs with MORE than two covariate groups:
 // up to 16 groups (distinct rows of the design matrix: a few conditions, 2x2 ... 2x2x2x2 factorials), D <= 4
-// covariates, K <= 31 cell types, fp32, one warp per chain.
+// covariates, fp32, one warp per chain; K <= 31 cell types with one cell type per lane (NS = 1), K <= 62 with two
+// (NS = 2: lane l owns the columns l and 32 + l; the row totals are column K).
 //
 // Same algorithm, Philox streams and per-parameter arithmetic as hmc_kernel (kernels_impl.cuh; reference:
 // sccoda/model/scCODA_model.py:276-315, :382-424) and the same pair / item formulation of the gradient as
@@ -17,7 +18,7 @@ namespace sccoda {
 
 struct MgTile {
     uint32_t cf, yv, ov, rows, el, xg, cnt, bnd;   // shared-memory byte offsets (MgPlan)
-    uint32_t yv_stride, ov_stride;                 // bytes per pair of groups
+    uint32_t yv_stride, ov_stride;                 // bytes per (pair of groups, column slot)
     int UP, UPmax;                                 // pairs of groups of THIS dataset / of the fullest dataset of the batch
     int N, NK, nbig;
     double lconst;
@@ -42,7 +43,7 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
 }
 
 // Staging: the packed dataset (include/sccoda_b200.h) re-laid lane-major, one block per pair of groups
-__device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl, int UPmax, MgTile& t) {
+__device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl, int UPmax, int NS, MgTile& t) {
     using T = float;
     const int N = a.dm.N, K = a.dm.K, D = a.dm.D, NK = a.dm.NK, Umax = a.Umax, NP = Umax * (K + 1);
     const int NT = a.NT, NOT = a.NOT;
@@ -53,9 +54,11 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
     t.N = N; t.NK = NK;
     t.UP = (a.U[b] + 1) >> 1;
     t.UPmax = UPmax;
-    // [up]: items, [UPmax + up]: odd counts of the fullest pair of the group pair, [2 UPmax]: elements with a count >= 6
+    const int CS = 32 * NS, NQ = UPmax * NS;
+    // [q]: items, [NQ + q]: odd counts of the fullest pair of (group pair, column slot) q = up * NS + s,
+    // [2 NQ]: elements with a count >= 6
     int* bounds = sp<int>((uint32_t)pl.bounds);
-    if (threadIdx.x < 2 * UPmax + 1) bounds[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < 2 * NQ + 1; i += blockDim.x) bounds[i] = 0;
     const int* rstart = a.rstart + (size_t)b * (Umax + 1);
     float* cnt = sp<float>((uint32_t)pl.cnt);
     if (threadIdx.x < 2 * UPmax) {
@@ -73,16 +76,17 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
     float* yv = sp<float>((uint32_t)pl.yv);
     float* ov = sp<float>((uint32_t)pl.ov);
     const T* pcoef = static_cast<const T*>(a.pcoef) + (size_t)b * NP * 6;
-    // rational coefficients: cf[up][j][lane] = (pair (2 up, lane), pair (2 up + 1, lane)); lane K = row totals
-    for (int i = threadIdx.x; i < UPmax * 6 * 32 * 2; i += blockDim.x) {
-        const int h = i & 1, lane = (i >> 1) & 31, r = i >> 6, up = r / 6, j = r - up * 6, u = 2 * up + h;
+    // rational coefficients: cf[q][j][lane] = (pair (2 up, col), pair (2 up + 1, col)), col = 32 s + lane; col K = row totals
+    for (int i = threadIdx.x; i < NQ * 6 * 32 * 2; i += blockDim.x) {
+        const int h = i & 1, lane = (i >> 1) & 31, r = i >> 6, q = r / 6, j = r - q * 6, up = q / NS, col = (q - up * NS) * 32 + lane;
+        const int u = 2 * up + h;
         float v = 0.0f;
-        if (lane <= K && u < Umax) v = pcoef[(lane < K ? u * K + lane : Umax * K + u) * 6 + j];
+        if (col <= K && u < Umax) v = pcoef[(col < K ? u * K + col : Umax * K + u) * 6 + j];
         cf[i] = v;
     }
     // item and odd counts: padding is the count 6, which contributes psi(c+6) - psi(c+6) = 0
-    for (int i = threadIdx.x; i < UPmax * NT * kItemR * 64; i += blockDim.x) yv[i] = 6.0f;
-    for (int i = threadIdx.x; i < UPmax * NOT * 64; i += blockDim.x) ov[i] = 6.0f;
+    for (int i = threadIdx.x; i < NQ * NT * kItemR * 64; i += blockDim.x) yv[i] = 6.0f;
+    for (int i = threadIdx.x; i < NQ * NOT * 64; i += blockDim.x) ov[i] = 6.0f;
     __syncthreads();
     const T* iy = static_cast<const T*>(a.iy) + (size_t)b * kItemR * a.NImax;
     const uint16_t* ipair = a.ipair + (size_t)b * a.NImax;
@@ -93,9 +97,9 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
         const int p = ipair[it], tt = ipos[it] - p * a.NF;
         int u, col;
         mg_pair_to_col(p, K, Umax, u, col);
-        const int up = u >> 1;
-        yv[(((up * NT + tt) * kItemR + j) * 32 + col) * 2 + (u & 1)] = iy[j * a.NImax + it];
-        if (j == 0) atomicMax(&bounds[up], tt + 1);
+        const int q = (u >> 1) * NS + (col >> 5);
+        yv[(((q * NT + tt) * kItemR + j) * 32 + (col & 31)) * 2 + (u & 1)] = iy[j * a.NImax + it];
+        if (j == 0) atomicMax(&bounds[q], tt + 1);
     }
     const int NG = a.NG[b];
     const T* oy = static_cast<const T*>(a.oy) + (size_t)b * a.NOmax;
@@ -103,11 +107,11 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
         const uint32_t od = a.odesc[(size_t)b * a.NGmax + q];
         int u, col;
         mg_pair_to_col(a.opair[(size_t)b * a.NGmax + q], K, Umax, u, col);
-        const int up = u >> 1;
-        for (int tt = 0; tt < (int)(od >> 16); ++tt) ov[((up * NOT + tt) * 32 + col) * 2 + (u & 1)] = oy[(od & 0xffffu) + tt];
-        atomicMax(&bounds[UPmax + up], (int)(od >> 16));
+        const int qq = (u >> 1) * NS + (col >> 5);
+        for (int tt = 0; tt < (int)(od >> 16); ++tt) ov[((qq * NOT + tt) * 32 + (col & 31)) * 2 + (u & 1)] = oy[(od & 0xffffu) + tt];
+        atomicMax(&bounds[NQ + qq], (int)(od >> 16));
     }
-    // value pass, rows and elements: as in cc_stage (hmc_cc.cuh), concentration slot = group * 32 + column
+    // value pass, rows and elements: as in cc_stage (hmc_cc.cuh), concentration slot = group * CS + column
     float4* rows = sp<float4>((uint32_t)pl.rows);
     const T* ntot = static_cast<const T*>(a.ntot) + (size_t)b * N;
     const int* grp = a.grp + (size_t)b * N;
@@ -116,7 +120,7 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
         const double nn = (double)ntot[n];
         const double lg = lgamma(nn);
         const double rc = nn >= 6.0 ? lg - ((nn - 0.5) * log(nn) - nn + 0.91893853320467274178) : lg;
-        rows[n] = make_float4((float)nn, (float)rc, __int_as_float(grp[n] * 32 + K), 0.0f);
+        rows[n] = make_float4((float)nn, (float)rc, __int_as_float(grp[n] * CS + K), 0.0f);
         lg_sum += lg;
     }
     double* red = sp<double>((uint32_t)pl.red);
@@ -145,143 +149,207 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
                 const int uk = (int)(eidx[e] & 0xffffu);
                 const int u = uk / K;
                 const int dst = big ? ib + __popc(mb & lt) : is + __popc(ms & lt);
-                el[dst] = make_float4(y, eycst[e], __int_as_float(u * 32 + (uk - u * K)), 1.0f / y);
+                el[dst] = make_float4(y, eycst[e], __int_as_float(u * CS + (uk - u * K)), 1.0f / y);
             }
             ib += __popc(mb);
             is += __popc(ms);
         }
-        if (lane == 0) bounds[2 * UPmax] = nbig;
+        if (lane == 0) bounds[2 * NQ] = nbig;
     }
     __syncthreads();
-    t.nbig = bounds[2 * UPmax];
+    t.nbig = bounds[2 * NQ];
     t.lconst = a.lconst[b] - (((red[0] + red[1]) + red[2]) + red[3]);
 }
 
-// The parameters a lane owns: alpha_k and, per covariate, b_offset_dk, ind_raw_dk (zero on the reference lane and on
-// lanes >= K) and sigma_d (uniform).
-template <int D>
+// The parameters a lane owns: per column slot s (cell type 32 s + lane) alpha and, per covariate, b_offset and
+// ind_raw (zero on the reference column and on columns >= K), and sigma_d (uniform).
+template <int D, int NS>
 struct MgVec {
-    float a, b[D], i[D], s[D];
+    float a[NS], b[NS][D], i[NS][D], s[D];
 };
-template <int D>
-__device__ __forceinline__ MgVec<D> mg_zero() {
-    MgVec<D> v;
-    v.a = 0.0f;
+template <int D, int NS>
+__device__ __forceinline__ MgVec<D, NS> mg_zero() {
+    MgVec<D, NS> v;
 #pragma unroll
-    for (int d = 0; d < D; ++d) v.b[d] = v.i[d] = v.s[d] = 0.0f;
+    for (int d = 0; d < D; ++d) v.s[d] = 0.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        v.a[s] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) v.b[s][d] = v.i[s][d] = 0.0f;
+    }
     return v;
 }
 // y = f x + y
-template <int D>
-__device__ __forceinline__ void mg_axpy(MgVec<D>& y, float f, const MgVec<D>& x) {
-    y.a = fmaf(f, x.a, y.a);
+template <int D, int NS>
+__device__ __forceinline__ void mg_axpy(MgVec<D, NS>& y, float f, const MgVec<D, NS>& x) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-        y.b[d] = fmaf(f, x.b[d], y.b[d]);
-        y.i[d] = fmaf(f, x.i[d], y.i[d]);
-        y.s[d] = fmaf(f, x.s[d], y.s[d]);
+    for (int d = 0; d < D; ++d) y.s[d] = fmaf(f, x.s[d], y.s[d]);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        y.a[s] = fmaf(f, x.a[s], y.a[s]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            y.b[s][d] = fmaf(f, x.b[s][d], y.b[s][d]);
+            y.i[s][d] = fmaf(f, x.i[s][d], y.i[s][d]);
+        }
     }
 }
 
+template <int NS>
 struct MgLane {
-    int K;
-    bool has, active;    // lane < K; lane < K and lane != ref
+    int K;                     // the row totals are column K = 32 ks() + kl()
+    bool has[NS], active[NS];  // column < K; column < K and column != ref
+    __device__ __forceinline__ int ks() const { return NS == 1 ? 0 : K >> 5; }
+    __device__ __forceinline__ int kl() const { return NS == 1 ? K : K & 31; }
+    __device__ __forceinline__ uint32_t hasmask() const {
+        uint32_t m = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) m |= has[s] ? 1u << s : 0u;
+        return m;
+    }
 };
 
 // Gradient of the log-density at q, pair / item formulation; the concentrations of every group are left
-// in the chain's shared-memory slots pc[group * 32 + column] (column K: S_u) for the value pass.
-template <int D>
-__device__ __forceinline__ MgVec<D> mg_grad(const MgTile& t, const MgLane& ln, const MgVec<D>& q, uint32_t pc_off, int lane) {
-    float id[D], bet[D], tg[D];
+// in the chain's shared-memory slots pc[group * 32 NS + column] (column K: S_u) for the value pass.
+template <int D, int NS>
+__device__ __forceinline__ MgVec<D, NS> mg_grad(const MgTile& t, const MgLane<NS>& ln, const MgVec<D, NS>& q, uint32_t pc_off,
+                                                int lane) {
+    float id[NS][D], bet[NS][D], tg[NS][D], ga[NS];
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-        id[d] = ln.active ? sigmoid_stable(50.0f * q.i[d]) : 0.0f;            // (:724-734)
-        bet[d] = id[d] * q.s[d] * q.b[d];
-        tg[d] = 0.0f;
+    for (int s = 0; s < NS; ++s) {
+        ga[s] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            id[s][d] = ln.active[s] ? sigmoid_stable(50.0f * q.i[s][d]) : 0.0f;            // (:724-734)
+            bet[s][d] = id[s][d] * q.s[d] * q.b[s][d];
+            tg[s][d] = 0.0f;
+        }
     }
-    float ga = 0.0f;
     uint32_t cf_off = t.cf + lane * 8, yv_off = t.yv + lane * 8, ov_off = t.ov + lane * 8, xg_off = t.xg;
     uint32_t pcw = pc_off + lane * 4;
     const float* cnt = sp<float>(t.cnt);
     const int* bnd = sp<int>(t.bnd);
+    const int n_q = t.UPmax * NS;
     __syncwarp();
 #pragma unroll 1
     for (int up = 0; up < t.UP; ++up) {
         const f32x2* xg = sp<f32x2>(xg_off);
-        f32x2 lin = dup2(q.a);
+        const bool empty_hi = cnt[2 * up + 1] == 0.0f;                            // empty slot of an odd group count
+        f32x2 c[NS];
+        float c0[NS], c1[NS], s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) lin = fma2(xg[d], dup2(bet[d]), lin);
-        f32x2 c = exp2_acc(lin);                                                  // (:743)
-        if (cnt[2 * up + 1] == 0.0f) c = pk2(lo2(c), 1.0f);                       // empty slot of an odd group count
-        const float c0 = ln.has ? lo2(c) : 0.0f, c1 = ln.has ? hi2(c) : 0.0f;
-        const float S = warp_sum2(c0, c1, lane);                                  // lanes 0..15: S_0, lanes 16..31: S_1
+        for (int s = 0; s < NS; ++s) {
+            f32x2 lin = dup2(q.a[s]);
+#pragma unroll
+            for (int d = 0; d < D; ++d) lin = fma2(xg[d], dup2(bet[s][d]), lin);
+            c[s] = exp2_acc(lin);                                                 // (:743)
+            if (empty_hi) c[s] = pk2(lo2(c[s]), 1.0f);
+            c0[s] = ln.has[s] ? lo2(c[s]) : 0.0f;
+            c1[s] = ln.has[s] ? hi2(c[s]) : 0.0f;
+            s0 += c0[s];
+            s1 += c1[s];
+        }
+        const float S = warp_sum2(s0, s1, lane);                                  // lanes 0..15: S_0, lanes 16..31: S_1
         const float So = __shfl_xor_sync(0xffffffffu, S, 16);
-        if (lane == ln.K) c = lane < 16 ? pk2(S, So) : pk2(So, S);
-        *sp<float>(pcw) = lo2(c);
-        *sp<float>(pcw + 128) = hi2(c);
-        // reference point of the items: x6 = c + 5.5, w6 = 1/x6, a = w6^5, nb = -5 (psi(c+6) - ln x6)
-        const f32x2 cm = add2(c, dup2(-0.5f));
-        const f32x2 w6 = rcp2(add2(c, dup2(5.5f)));
-        const f32x2 w62 = mul2(w6, w6);
-        const f32x2 a5 = mul2(mul2(w62, w62), w6);
-        const f32x2 nb = mul2(psi_mid_acc2(w6, dup2(0.0f)), dup2(-(float)SCCODA_ITEM_R));
-        // brackets Br = rational sum_i W_i/(c+i) + items + odd counts, both groups at once
-        f32x2 br = pair_rational2(c, sp<f32x2>(cf_off));
-        const f32x2* yv = sp<f32x2>(yv_off);
-        const int nt = bnd[up], n_odd = bnd[t.UPmax + up];
+        f32x2 br[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (s == ln.ks() && lane == ln.kl()) c[s] = lane < 16 ? pk2(S, So) : pk2(So, S);
+            *sp<float>(pcw + s * 128) = lo2(c[s]);
+            *sp<float>(pcw + s * 128 + NS * 128) = hi2(c[s]);
+            // reference point of the items: x6 = c + 5.5, w6 = 1/x6, a = w6^5, nb = -5 (psi(c+6) - ln x6)
+            const f32x2 cm = add2(c[s], dup2(-0.5f));
+            const f32x2 w6 = rcp2(add2(c[s], dup2(5.5f)));
+            const f32x2 w62 = mul2(w6, w6);
+            const f32x2 a5 = mul2(mul2(w62, w62), w6);
+            const f32x2 nb = mul2(psi_mid_acc2(w6, dup2(0.0f)), dup2(-(float)SCCODA_ITEM_R));
+            // brackets Br = rational sum_i W_i/(c+i) + items + odd counts, both groups at once
+            f32x2 b2 = pair_rational2(c[s], sp<f32x2>(cf_off));
+            const f32x2* yv = sp<f32x2>(yv_off);
+            const int nt = bnd[up * NS + s], n_odd = bnd[n_q + up * NS + s];
 #pragma unroll 1
-        for (int tt = 0; tt < nt; ++tt, yv += SCCODA_ITEM_R * 32) br = add2(br, item_eval2(cm, a5, nb, yv));
-        if (n_odd > 0) {
-            // counts below 6 that are not in {0..5} (the 0.5 pseudocount, non-integer data), one by one
-            const f32x2 x6 = add2(c, dup2(5.5f));
-            const f32x2 nref = fma2(lg2_2(x6), dup2(-SCCODA_LN2F), mul2(nb, dup2(1.0f / (float)SCCODA_ITEM_R)));   // -psi(c+6)
-            yv = sp<f32x2>(ov_off);
+            for (int tt = 0; tt < nt; ++tt, yv += SCCODA_ITEM_R * 32) b2 = add2(b2, item_eval2(cm, a5, nb, yv));
+            if (n_odd > 0) {
+                // counts below 6 that are not in {0..5} (the 0.5 pseudocount, non-integer data), one by one
+                const f32x2 x6 = add2(c[s], dup2(5.5f));
+                const f32x2 nref = fma2(lg2_2(x6), dup2(-SCCODA_LN2F), mul2(nb, dup2(1.0f / (float)SCCODA_ITEM_R)));   // -psi(c+6)
+                yv = sp<f32x2>(ov_off);
 #pragma unroll 1
-            for (int tt = 0; tt < n_odd; ++tt, yv += 32) br = add2(br, add2(psi_any2(add2(c, *yv)), nref));
+                for (int tt = 0; tt < n_odd; ++tt, yv += 32) b2 = add2(b2, add2(psi_any2(add2(c[s], *yv)), nref));
+            }
+            br[s] = b2;
+            cf_off += 6 * 32 * 8; yv_off += t.yv_stride; ov_off += t.ov_stride;
         }
         // d logp / d log c_uk = c_uk (Br_uk - Br_total(u)), chain rule through alpha and the effects
-        const float bt0 = __shfl_sync(0xffffffffu, lo2(br), ln.K), bt1 = __shfl_sync(0xffffffffu, hi2(br), ln.K);
-        const float G0 = c0 * (lo2(br) - bt0), G1 = c1 * (hi2(br) - bt1);        // c0 = c1 = 0 on lanes >= K
-        ga += G0 + G1;
+        f32x2 brt = br[0];
+#pragma unroll
+        for (int s = 1; s < NS; ++s)
+            if (s == ln.ks()) brt = br[s];
+        const float bt0 = __shfl_sync(0xffffffffu, lo2(brt), ln.kl()), bt1 = __shfl_sync(0xffffffffu, hi2(brt), ln.kl());
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float G0 = c0[s] * (lo2(br[s]) - bt0), G1 = c1[s] * (hi2(br[s]) - bt1);   // c0 = c1 = 0 on columns >= K
+            ga[s] += G0 + G1;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const f32x2 xv = xg[d];
+                tg[s][d] = fmaf(lo2(xv), G0, fmaf(hi2(xv), G1, tg[s][d]));
+            }
+        }
+        xg_off += D * 8; pcw += NS * 256;
+    }
+    MgVec<D, NS> g;
+    float sg[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) sg[d] = 0.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        g.a[s] = fmaf(q.a[s], -0.04f, ga[s]);                                      // d/d alpha_k
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const f32x2 xv = xg[d];
-            tg[d] = fmaf(lo2(xv), G0, fmaf(hi2(xv), G1, tg[d]));
+            const float tgi = tg[s][d] * id[s][d];                                 // id == 0 on inactive columns
+            g.b[s][d] = fmaf(tgi, q.s[d], -q.b[s][d]);                             // d/d b_offset_dk
+            g.i[s][d] = fmaf(tgi * q.s[d] * q.b[s][d], 50.0f * (1.0f - id[s][d]), -q.i[s][d]);   // d/d ind_raw_dk
+            sg[d] = fmaf(tgi, q.b[s][d], sg[d]);
         }
-        cf_off += 6 * 32 * 8; yv_off += t.yv_stride; ov_off += t.ov_stride; xg_off += D * 8; pcw += 256;
     }
-    MgVec<D> g;
-    g.a = fmaf(q.a, -0.04f, ga);                                               // d/d alpha_k
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        const float tgi = tg[d] * id[d];                                       // id == 0 on inactive lanes
-        g.b[d] = fmaf(tgi, q.s[d], -q.b[d]);                                   // d/d b_offset_dk
-        g.i[d] = fmaf(tgi * q.s[d] * q.b[d], 50.0f * (1.0f - id[d]), -q.i[d]); // d/d ind_raw_dk
         // d/d sigma_d: sum_k g_k ind_k b_offset_k - HalfCauchy term (zero prior gradient below 0 [TFP])
-        g.s[d] = warp_sum1(tgi * q.b[d]) - (q.s[d] >= 0.0f ? 2.0f * q.s[d] * rcp_fast(fmaf(q.s[d], q.s[d], 1.0f)) : 0.0f);
+        g.s[d] = warp_sum1(sg[d]) - (q.s[d] >= 0.0f ? 2.0f * q.s[d] * rcp_fast(fmaf(q.s[d], q.s[d], 1.0f)) : 0.0f);
     }
     return g;
 }
 
 // lane's share of the parameter priors (:703-741) and the HalfCauchy support flag, for mg_value
-template <int D>
-__device__ __forceinline__ float mg_prior(const MgVec<D>& q, int lane, bool& neg_sigma) {
-    float prior = q.a * q.a * -0.02f, slab = 0.0f, cauchy = 0.0f;
+template <int D, int NS>
+__device__ __forceinline__ float mg_prior(const MgVec<D, NS>& q, int lane, bool& neg_sigma) {
+    float quad = 0.0f, slab = 0.0f, cauchy = 0.0f;
     neg_sigma = false;
 #pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        quad = fmaf(q.a[s], q.a[s], quad);
+#pragma unroll
+        for (int d = 0; d < D; ++d) slab += fmaf(q.b[s][d], q.b[s][d], q.i[s][d] * q.i[s][d]);
+    }
+#pragma unroll
     for (int d = 0; d < D; ++d) {
-        slab += fmaf(q.b[d], q.b[d], q.i[d] * q.i[d]);
         if (q.s[d] >= 0.0f) cauchy += log1pf(q.s[d] * q.s[d]);
         else neg_sigma = true;
     }
-    prior = fmaf(-0.5f, slab, prior);
+    float prior = fmaf(-0.5f, slab, quad * -0.02f);
     if (lane == 0) prior -= cauchy;
     return prior;
 }
 
 // Value of the log-density from the concentrations the last gradient evaluation left in pc (same terms, guards and
-// precision strategy as cc_value / dm_value); `prior` is the lane's share of the parameter priors.
-static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off, bool has, float prior, bool neg_sigma, int K, int lane) {
+// precision strategy as cc_value / dm_value); `prior` is the lane's share of the parameter priors, bit s of
+// `hasmask` says whether the lane's column slot s holds a cell type.
+template <int NS>
+static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off, uint32_t hasmask, float prior, bool neg_sigma,
+                                               int lane) {
+    constexpr int CS = 32 * NS;
     const float* pc = sp<float>(pc_off);
     __syncwarp();
     double lp = (double)prior;
@@ -289,14 +357,18 @@ static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off,
     // Guard (numerics): beyond c_max the lgamma differences have lost all precision => NaN => rejected.
     const float c_max = 1e6f, c_joint = SCCODA_C_JOINT;
     bool need_fix = false, bad = false;
-    if (has) {
+    {
         const float* cnt = sp<float>(t.cnt);
         float acc = 0.0f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (!((hasmask >> s) & 1u)) continue;
 #pragma unroll 1
-        for (int u = 0; u < 2 * t.UP; ++u) {
-            const float cu = pc[u * 32 + lane];
-            if (cu < c_joint) acc = fmaf(-cnt[u], lgamma_pos(cu), acc); else need_fix = true;
-            bad = bad || !(cu <= c_max);
+            for (int u = 0; u < 2 * t.UP; ++u) {
+                const float cu = pc[u * CS + s * 32 + lane];
+                if (cu < c_joint) acc = fmaf(-cnt[u], lgamma_pos(cu), acc); else need_fix = true;
+                bad = bad || !(cu <= c_max);
+            }
         }
         lp += (double)acc;
     }
@@ -355,67 +427,111 @@ static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off,
     return lp;
 }
 
+// Per-lane bookkeeping shared by the HMC and the NUTS kernel: which columns the lane owns and where its parameters
+// sit in the flat state vector (order of scCODA_model.py:692-693): sigma_d[D] | b_offset[D][K-1] | ind_raw[D][K-1] |
+// alpha[K]
+template <int D, int NS>
+struct MgMap {
+    MgLane<NS> ln;
+    int ix_a[NS], ix_b[NS], ix_i[NS], K1;
+
+    __device__ __forceinline__ void init(int K, int ref, int lane) {
+        K1 = K - 1;
+        ln.K = K;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int col = s * 32 + lane;
+            ln.has[s] = col < K;
+            ln.active[s] = ln.has[s] && col != ref;
+            const int jj = col - (col > ref);
+            ix_b[s] = D + jj;
+            ix_i[s] = D + D * K1 + jj;
+            ix_a[s] = D + 2 * D * K1 + col;
+        }
+    }
+    __device__ __forceinline__ MgVec<D, NS> gather(const float* v) const {   // flat shared-memory vector -> lane registers
+        MgVec<D, NS> r;
+#pragma unroll
+        for (int d = 0; d < D; ++d) r.s[d] = v[d];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            r.a[s] = ln.has[s] ? v[ix_a[s]] : 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                r.b[s][d] = ln.active[s] ? v[ix_b[s] + d * K1] : 0.0f;
+                r.i[s][d] = ln.active[s] ? v[ix_i[s] + d * K1] : 0.0f;
+            }
+        }
+        return r;
+    }
+    __device__ __forceinline__ void scatter(float* v, const MgVec<D, NS>& r, int lane) const {   // lane registers -> flat vector
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            if (lane == 0) v[d] = r.s[d];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (ln.has[s]) v[ix_a[s]] = r.a[s];
+            if (ln.active[s]) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    v[ix_b[s] + d * K1] = r.b[s][d];
+                    v[ix_i[s] + d * K1] = r.i[s][d];
+                }
+            }
+        }
+    }
+};
+
+// per-lane part of a dot product over the flat parameter vector (sigma_d is replicated: lane 0 counts it)
+template <int D, int NS>
+__device__ __forceinline__ float mg_dot(const MgVec<D, NS>& x, const MgVec<D, NS>& y, int lane) {
+    float v = 0.0f, sv = 0.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        v = fmaf(x.a[s], y.a[s], v);
+#pragma unroll
+        for (int d = 0; d < D; ++d) v = fmaf(x.b[s][d], y.b[s][d], fmaf(x.i[s][d], y.i[s][d], v));
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) sv = fmaf(x.s[d], y.s[d], sv);
+    return lane == 0 ? v + sv : v;
+}
+
+// resident CTAs of 128 threads per SM the kernels are compiled for (register caps)
+constexpr int mg_hmc_ctas(int D, int NS) { return NS == 1 ? (D == 1 ? 6 : (D == 2 ? 5 : (D == 3 ? 4 : 3))) : (D == 1 ? 4 : (D == 2 ? 3 : 2)); }
+constexpr int mg_nuts_ctas(int D, int NS) { return NS == 1 ? (D == 1 ? 4 : (D <= 2 ? 3 : 2)) : (D == 1 ? 3 : (D == 2 ? 2 : 1)); }
+
 // ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : (D == 3 ? 4 : 3))) hmc_mg_kernel(const __grid_constant__ KArgs a) {
+template <int D, int NS>
+__global__ void __launch_bounds__(128, mg_hmc_ctas(D, NS)) hmc_mg_kernel(const __grid_constant__ KArgs a) {
     using T = float;
+    using V = MgVec<D, NS>;
     const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
     const int cpc = blockDim.x >> 5;
     const int ctas_per_ds = (a.C + cpc - 1) / cpc;
     const int b = blockIdx.x / ctas_per_ds;
     const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
-    const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P;
+    const int K = a.dm.K, P = a.dm.P;
     const int UPmax = (a.Umax + 1) >> 1;
-    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, a.NT, a.NOT, 0);
+    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, NS, a.NT, a.NOT, 0);
     MgTile tile;
-    mg_stage(a, b, pl, UPmax, tile);
+    mg_stage(a, b, pl, UPmax, NS, tile);
     if (c >= a.C) return;
     const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
     const uint32_t pc_off = pin_u32(chain_off + (uint32_t)pl.pc);
     T* const vec = sp<T>(pin_u32(chain_off + (uint32_t)pl.vec));   // one flat state vector: momentum transpose, carry in / out
     const size_t chain = (size_t)b * a.C + c;
     const RngKey key{(uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), a.chain_id0 + (uint32_t)chain};
-    const int ref = a.ref[b];
-
-    MgLane ln;
-    ln.K = K;
-    ln.has = lane < K;
-    ln.active = ln.has && lane != ref;
-    // flat indices of the lane's parameters (order of scCODA_model.py:692-693): sigma_d[D] | b_offset[D][K-1] |
-    // ind_raw[D][K-1] | alpha[K]
-    const int jj = lane - (lane > ref);
-    const int ix_b = D + jj, ix_i = D + D * K1 + jj, ix_a = D + 2 * D * K1 + lane;
-
-    auto gather = [&](const T* v) {               // flat shared-memory vector -> lane registers
-        MgVec<D> r;
-        r.a = ln.has ? v[ix_a] : T(0);
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            r.s[d] = v[d];
-            r.b[d] = ln.active ? v[ix_b + d * K1] : T(0);
-            r.i[d] = ln.active ? v[ix_i + d * K1] : T(0);
-        }
-        return r;
-    };
-    auto scatter = [&](T* v, const MgVec<D>& r) {    // lane registers -> flat vector (shared or global)
-        if (ln.has) v[ix_a] = r.a;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            if (lane == 0) v[d] = r.s[d];
-            if (ln.active) {
-                v[ix_b + d * K1] = r.b[d];
-                v[ix_i + d * K1] = r.i[d];
-            }
-        }
-    };
+    MgMap<D, NS> mp;
+    mp.init(K, a.ref[b], lane);
 
     Adapt<T> ad;
     load_chain_state<T>(a, chain, vec, ad, lane, 32);
     __syncwarp();
-    MgVec<D> thc = gather(vec);                    // current state
-    MgVec<D> gc = mg_zero<D>();                    // its gradient
+    V thc = mp.gather(vec);                        // current state
+    V gc = mg_zero<D, NS>();                       // its gradient
     const int L = a.num_leapfrog;
     const double log_target = log(a.target_accept);
     T* draws = static_cast<T*>(a.draws) + chain * (size_t)a.num_results * P;
@@ -429,7 +545,7 @@ __global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : (D == 3 ? 4 : 
         const bool boot = t < a.step_begin;
         const T eps = ad.eps;
         T kin = T(0);
-        MgVec<D> q = thc, m = mg_zero<D>();
+        V q = thc, m = mg_zero<D, NS>();
         if (!boot) {
             // momentum draw in the flat parameter order (the stream contract of philox.cuh), regrouped by cell type
             __syncwarp();
@@ -441,42 +557,39 @@ __global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : (D == 3 ? 4 : 
             }
             __syncwarp();
             // first half kick and first drift: q1 = q0 + eps (p + eps/2 grad(q0))
-            m = gather(vec);
-            mg_axpy<D>(m, T(0.5) * eps, gc);
-            mg_axpy<D>(q, eps, m);
+            m = mp.gather(vec);
+            mg_axpy<D, NS>(m, T(0.5) * eps, gc);
+            mg_axpy<D, NS>(q, eps, m);
         }
         const int nl = boot ? 1 : L;
-        MgVec<D> gr;
+        V gr;
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
-            gr = mg_grad<D>(tile, ln, q, pc_off, lane);
+            gr = mg_grad<D, NS>(tile, mp.ln, q, pc_off, lane);
             if (a.dm.freeze) {                     // SimpleModel: sigma_d and ind_raw stay where they are
 #pragma unroll
-                for (int d = 0; d < D; ++d) gr.s[d] = gr.i[d] = T(0);
+                for (int d = 0; d < D; ++d) {
+                    gr.s[d] = T(0);
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) gr.i[s][d] = T(0);
+                }
             }
             if (!boot) {
                 const bool last = (l == nl - 1);
-                mg_axpy<D>(m, last ? T(0.5) * eps : eps, gr);
-                if (!last) mg_axpy<D>(q, eps, m);
+                mg_axpy<D, NS>(m, last ? T(0.5) * eps : eps, gr);
+                if (!last) mg_axpy<D, NS>(q, eps, m);
             }
         }
         // value at the end point, from the concentrations of the last gradient evaluation; priors (:703-741), the
         // theta-independent constants live in lconst, parameters a lane does not own are zero
         bool neg_sigma;
-        const float prior = mg_prior<D>(q, lane, neg_sigma);
-        const double lp_new = mg_value(tile, pc_off, ln.has, prior, neg_sigma, K, lane);
+        const float prior = mg_prior<D, NS>(q, lane, neg_sigma);
+        const double lp_new = mg_value<NS>(tile, pc_off, mp.ln.hasmask(), prior, neg_sigma, lane);
         bool acc = true;
         double lar = 0.0;
         if (!boot) {
-            // kinetic energies: the momenta of sigma_d are replicated, count them once
-            float k1 = m.a * m.a, ks = 0.0f;
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                k1 += fmaf(m.b[d], m.b[d], m.i[d] * m.i[d]);
-                ks = fmaf(m.s[d], m.s[d], ks);
-            }
-            kin -= k1;
-            if (lane == 0) kin -= ks;
+            // kinetic energies: sum p0^2 over the flat vector minus the lane's share of the end momenta
+            kin -= mg_dot<D, NS>(m, m, lane);
             double dkin = (double)kin;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) dkin += __shfl_xor_sync(0xffffffffu, dkin, o);
@@ -501,131 +614,104 @@ __global__ void __launch_bounds__(128, D == 1 ? 6 : (D == 2 ? 5 : (D == 3 ? 4 : 
         }
         const int r = t - a.num_burnin;
         if (r >= 0 && a.store_draws) {
-            scatter(draws + (size_t)r * P, thc);
+            mp.scatter(draws + (size_t)r * P, thc, lane);
             if (lane == 0)
                 write_stats<T>(stats + (size_t)r * SCCODA_NSTAT, lp_cur, lar, acc, traced_eps, lar < -1000.0, L,
                                CUDART_NAN, false);
         }
     }
     __syncwarp();
-    scatter(vec, thc);
+    mp.scatter(vec, thc, lane);
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K3mg — NUTS for the same designs: the iterative tree of nuts_kernel / nuts_cc_kernel ([TFP] NoUTurnSampler.one_step as
-// restated in SURVEY §8c) on the lane-per-cell-type state.  A stored vector of the tree is D float4 per lane
-// (3 D + 1 parameters) in shared memory; the leaf being integrated lives in registers.
+// restated in SURVEY §8c) on the lane-per-cell-type state.  A stored vector of the tree is mg_vec_quads(D, NS) float4
+// per lane (NS (1 + 2 D) + D parameters) in shared memory; the leaf being integrated lives in registers.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double mg_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-template <int D>
-__device__ __forceinline__ MgVec<D> mg_ld(const float4* slot) {
-    float f[4 * D];
+template <int D, int NS>
+__device__ __forceinline__ MgVec<D, NS> mg_ld(const float4* slot) {
+    constexpr int NQ = mg_vec_quads(D, NS);
+    float f[4 * NQ];
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
+    for (int k = 0; k < NQ; ++k) {
         const float4 v = slot[32 * k];
         f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
     }
-    MgVec<D> r;
-    r.a = f[0];
+    MgVec<D, NS> r;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-        r.b[d] = f[1 + d];
-        r.i[d] = f[1 + D + d];
-        r.s[d] = f[1 + 2 * D + d];
+    for (int d = 0; d < D; ++d) r.s[d] = f[d];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        r.a[s] = f[D + s * (1 + 2 * D)];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            r.b[s][d] = f[D + s * (1 + 2 * D) + 1 + d];
+            r.i[s][d] = f[D + s * (1 + 2 * D) + 1 + D + d];
+        }
     }
     return r;
 }
-template <int D>
-__device__ __forceinline__ void mg_st(float4* slot, const MgVec<D>& r) {
-    float f[4 * D];
+template <int D, int NS>
+__device__ __forceinline__ void mg_st(float4* slot, const MgVec<D, NS>& r) {
+    constexpr int NQ = mg_vec_quads(D, NS);
+    float f[4 * NQ];
 #pragma unroll
-    for (int k = 0; k < 4 * D; ++k) f[k] = 0.0f;
-    f[0] = r.a;
+    for (int k = 0; k < 4 * NQ; ++k) f[k] = 0.0f;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-        f[1 + d] = r.b[d];
-        f[1 + D + d] = r.i[d];
-        f[1 + 2 * D + d] = r.s[d];
+    for (int d = 0; d < D; ++d) f[d] = r.s[d];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        f[D + s * (1 + 2 * D)] = r.a[s];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            f[D + s * (1 + 2 * D) + 1 + d] = r.b[s][d];
+            f[D + s * (1 + 2 * D) + 1 + D + d] = r.i[s][d];
+        }
     }
 #pragma unroll
-    for (int k = 0; k < D; ++k) slot[32 * k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+    for (int k = 0; k < NQ; ++k) slot[32 * k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
 }
-// per-lane part of a dot product over the flat parameter vector (sigma_d is replicated: lane 0 counts it)
-template <int D>
-__device__ __forceinline__ float mg_dot(const MgVec<D>& x, const MgVec<D>& y, int lane) {
-    float v = x.a * y.a, sv = 0.0f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        v = fmaf(x.b[d], y.b[d], fmaf(x.i[d], y.i[d], v));
-        sv = fmaf(x.s[d], y.s[d], sv);
-    }
-    return lane == 0 ? v + sv : v;
-}
-template <int D>
-__global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_kernel(const __grid_constant__ KArgs a) {
+
+template <int D, int NS>
+__global__ void __launch_bounds__(128, mg_nuts_ctas(D, NS)) nuts_mg_kernel(const __grid_constant__ KArgs a) {
     using T = float;
-    using V = MgVec<D>;
+    using V = MgVec<D, NS>;
+    constexpr int NQ = mg_vec_quads(D, NS);
     const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
     const int cpc = blockDim.x >> 5;
     const int ctas_per_ds = (a.C + cpc - 1) / cpc;
     const int b = blockIdx.x / ctas_per_ds;
     const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
-    const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P, maxd = a.max_depth;
+    const int K = a.dm.K, P = a.dm.P, maxd = a.max_depth;
     const int UPmax = (a.Umax + 1) >> 1;
-    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, a.NT, a.NOT, 11 + 2 * (maxd + 1));
+    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, NS, a.NT, a.NOT, 11 + 2 * (maxd + 1));
     MgTile tile;
-    mg_stage(a, b, pl, UPmax, tile);
+    mg_stage(a, b, pl, UPmax, NS, tile);
     if (c >= a.C) return;
     const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
     const uint32_t pc_off = pin_u32(chain_off + (uint32_t)pl.pc);
     T* const vec = sp<T>(pin_u32(chain_off + (uint32_t)pl.vec));
     float4* const slots = sp<float4>(pin_u32(chain_off + (uint32_t)pl.slots)) + lane;   // slot k of this lane: slot(k)
-    auto slot = [&](int k) { return slots + 32 * D * k; };
+    auto slot = [&](int k) { return slots + 32 * NQ * k; };
     enum { S_CQ = 0, S_CG, S_LQ, S_LP, S_LG, S_RQ, S_RP, S_RG, S_SQ, S_SG, S_RHO, S_CKP };
     const int S_CKR = S_CKP + (maxd + 1);
     const size_t chain = (size_t)b * a.C + c;
     const RngKey key{(uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), a.chain_id0 + (uint32_t)chain};
-    const int ref = a.ref[b];
-
-    MgLane ln;
-    ln.K = K;
-    ln.has = lane < K;
-    ln.active = ln.has && lane != ref;
-    const int jj = lane - (lane > ref);
-    const int ix_b = D + jj, ix_i = D + D * K1 + jj, ix_a = D + 2 * D * K1 + lane;
-    auto gather = [&](const T* v) {
-        V r;
-        r.a = ln.has ? v[ix_a] : T(0);
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            r.s[d] = v[d];
-            r.b[d] = ln.active ? v[ix_b + d * K1] : T(0);
-            r.i[d] = ln.active ? v[ix_i + d * K1] : T(0);
-        }
-        return r;
-    };
-    auto scatter = [&](T* v, const V& r) {
-        if (ln.has) v[ix_a] = r.a;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            if (lane == 0) v[d] = r.s[d];
-            if (ln.active) {
-                v[ix_b + d * K1] = r.b[d];
-                v[ix_i + d * K1] = r.i[d];
-            }
-        }
-    };
+    MgMap<D, NS> mp;
+    mp.init(K, a.ref[b], lane);
 
     Adapt<T> ad;
     load_chain_state<T>(a, chain, vec, ad, lane, 32);
     __syncwarp();
-    V q = gather(vec), p = mg_zero<D>(), gq = mg_zero<D>(), rho_s = mg_zero<D>();
+    V q = mp.gather(vec), p = mg_zero<D, NS>(), gq = mg_zero<D, NS>(), rho_s = mg_zero<D, NS>();
     T* draws = static_cast<T*>(a.draws) + chain * (size_t)a.num_results * P;
     T* stats = static_cast<T*>(a.stats) + chain * (size_t)a.num_results * SCCODA_NSTAT;
 
@@ -647,10 +733,10 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_ke
                 vec[i] = pm;
             }
             __syncwarp();
-            const V pm = gather(vec), cq = mg_ld<D>(slot(S_CQ)), cg = mg_ld<D>(slot(S_CG));
-            mg_st<D>(slot(S_LQ), cq); mg_st<D>(slot(S_LP), pm); mg_st<D>(slot(S_LG), cg);
-            mg_st<D>(slot(S_RQ), cq); mg_st<D>(slot(S_RP), pm); mg_st<D>(slot(S_RG), cg);
-            mg_st<D>(slot(S_RHO), pm);
+            const V pm = mp.gather(vec), cq = mg_ld<D, NS>(slot(S_CQ)), cg = mg_ld<D, NS>(slot(S_CG));
+            mg_st<D, NS>(slot(S_LQ), cq); mg_st<D, NS>(slot(S_LP), pm); mg_st<D, NS>(slot(S_LG), cg);
+            mg_st<D, NS>(slot(S_RQ), cq); mg_st<D, NS>(slot(S_RP), pm); mg_st<D, NS>(slot(S_RG), cg);
+            mg_st<D, NS>(slot(S_RHO), pm);
             e0 = lp_cur - 0.5 * mg_sum_d((double)kin);
         }
         double l_lp = lp_cur, r_lp = lp_cur, c_lp = lp_cur, c_energy = e0, s_lp = lp_cur, s_en = e0;
@@ -666,10 +752,10 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_ke
             const T se = forward ? eps : -eps;
             double lqv = forward ? r_lp : l_lp;
             if (!boot) {
-                q = mg_ld<D>(slot(e_q));
-                p = mg_ld<D>(slot(e_p));
-                gq = mg_ld<D>(slot(e_g));
-                rho_s = mg_zero<D>();
+                q = mg_ld<D, NS>(slot(e_q));
+                p = mg_ld<D, NS>(slot(e_p));
+                gq = mg_ld<D, NS>(slot(e_g));
+                rho_s = mg_zero<D, NS>();
             }
             const unsigned n_leaves = 1u << depth;
             double w_s = -CUDART_INF;
@@ -677,44 +763,43 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_ke
 #pragma unroll 1
             for (unsigned leaf = 0; leaf < n_leaves && alive; ++leaf) {
                 if (!boot) {
-                    mg_axpy<D>(p, T(0.5) * se, gq);
-                    mg_axpy<D>(q, se, p);
+                    mg_axpy<D, NS>(p, T(0.5) * se, gq);
+                    mg_axpy<D, NS>(q, se, p);
                 }
-                gq = mg_grad<D>(tile, ln, q, pc_off, lane);
+                gq = mg_grad<D, NS>(tile, mp.ln, q, pc_off, lane);
                 if (a.dm.freeze) {
 #pragma unroll
-                    for (int d = 0; d < D; ++d) gq.s[d] = gq.i[d] = T(0);
+                    for (int d = 0; d < D; ++d) {
+                        gq.s[d] = T(0);
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) gq.i[s][d] = T(0);
+                    }
                 }
                 {
                     bool neg_sigma;
-                    const float prior = mg_prior<D>(q, lane, neg_sigma);
-                    lqv = mg_value(tile, pc_off, ln.has, prior, neg_sigma, K, lane);
+                    const float prior = mg_prior<D, NS>(q, lane, neg_sigma);
+                    lqv = mg_value<NS>(tile, pc_off, mp.ln.hasmask(), prior, neg_sigma, lane);
                 }
                 if (boot) break;
-                mg_axpy<D>(p, T(0.5) * se, gq);
-                mg_axpy<D>(rho_s, T(1), p);
-                const T kk = mg_dot<D>(p, p, lane);
+                mg_axpy<D, NS>(p, T(0.5) * se, gq);
+                mg_axpy<D, NS>(rho_s, T(1), p);
+                const T kk = mg_dot<D, NS>(p, p, lane);
                 leapfrogs += 1;
                 const int idx_max = __popc(leaf >> 1);
                 bool no_uturn = true;
                 if ((leaf & 1u) == 0u) {
-                    mg_st<D>(slot(S_CKP + idx_max), p);
-                    mg_st<D>(slot(S_CKR + idx_max), rho_s);
+                    mg_st<D, NS>(slot(S_CKP + idx_max), p);
+                    mg_st<D, NS>(slot(S_CKR + idx_max), rho_s);
                 } else {
                     const int n_chk = __ffs(~leaf) - 1;  // trailing ones
 #pragma unroll 1
                     for (int sidx = idx_max; sidx > idx_max - n_chk && no_uturn; --sidx) {
-                        const V cp = mg_ld<D>(slot(S_CKP + sidx));
-                        V span = mg_ld<D>(slot(S_CKR + sidx));
+                        const V cp = mg_ld<D, NS>(slot(S_CKP + sidx));
                         // span = rho_s - checkpoint rho + checkpoint momentum
-                        span.a = rho_s.a - span.a + cp.a;
-#pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            span.b[d] = rho_s.b[d] - span.b[d] + cp.b[d];
-                            span.i[d] = rho_s.i[d] - span.i[d] + cp.i[d];
-                            span.s[d] = rho_s.s[d] - span.s[d] + cp.s[d];
-                        }
-                        const double D1 = mg_sum_d((double)mg_dot<D>(span, cp, lane)), D2 = mg_sum_d((double)mg_dot<D>(span, p, lane));
+                        V span = rho_s;
+                        mg_axpy<D, NS>(span, T(-1), mg_ld<D, NS>(slot(S_CKR + sidx)));
+                        mg_axpy<D, NS>(span, T(1), cp);
+                        const double D1 = mg_sum_d((double)mg_dot<D, NS>(span, cp, lane)), D2 = mg_sum_d((double)mg_dot<D, NS>(span, p, lane));
                         if (!(D1 >= 0.0 && D2 >= 0.0)) no_uturn = false;
                     }
                 }
@@ -726,8 +811,8 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_ke
                 const double u = (double)rng_uniform<T>(key, leaf_serial++, (uint32_t)t, STREAM_NUTS_LEAF);
                 const double thresh = (w_new > -CUDART_INF) ? delta - w_new : CUDART_NAN;
                 if (nuts_log1m<T>(u) <= thresh) {
-                    mg_st<D>(slot(S_SQ), q);
-                    mg_st<D>(slot(S_SG), gq);
+                    mg_st<D, NS>(slot(S_SQ), q);
+                    mg_st<D, NS>(slot(S_SG), gq);
                     s_lp = lqv; s_en = energy;
                 }
                 w_s = w_new;
@@ -736,8 +821,8 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_ke
                 alive = (!divergent) && no_uturn;
             }
             if (boot) {
-                mg_st<D>(slot(S_CQ), q);
-                mg_st<D>(slot(S_CG), gq);
+                mg_st<D, NS>(slot(S_CQ), q);
+                mg_st<D, NS>(slot(S_CG), gq);
                 c_lp = lqv;
                 break;
             }
@@ -746,19 +831,19 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_ke
             if (isnan(thresh)) thresh = 0.0;
             const double u = (double)rng_uniform<T>(key, (uint32_t)depth, (uint32_t)t, STREAM_NUTS_TOP);
             if ((nuts_log1m<T>(u) <= thresh) && alive) {
-                mg_st<D>(slot(S_CQ), mg_ld<D>(slot(S_SQ)));
-                mg_st<D>(slot(S_CG), mg_ld<D>(slot(S_SG)));
+                mg_st<D, NS>(slot(S_CQ), mg_ld<D, NS>(slot(S_SQ)));
+                mg_st<D, NS>(slot(S_CG), mg_ld<D, NS>(slot(S_SG)));
                 c_lp = s_lp; c_energy = s_en; is_acc = true;
             }
             wsum = nuts_logaddexp<T>(wsum, tree_w);
-            mg_st<D>(slot(e_q), q);
-            mg_st<D>(slot(e_p), p);
-            mg_st<D>(slot(e_g), gq);
-            V rho = mg_ld<D>(slot(S_RHO));
-            mg_axpy<D>(rho, T(1), rho_s);
-            mg_st<D>(slot(S_RHO), rho);
-            const double D1 = mg_sum_d((double)mg_dot<D>(rho, mg_ld<D>(slot(S_LP)), lane));
-            const double D2 = mg_sum_d((double)mg_dot<D>(rho, mg_ld<D>(slot(S_RP)), lane));
+            mg_st<D, NS>(slot(e_q), q);
+            mg_st<D, NS>(slot(e_p), p);
+            mg_st<D, NS>(slot(e_g), gq);
+            V rho = mg_ld<D, NS>(slot(S_RHO));
+            mg_axpy<D, NS>(rho, T(1), rho_s);
+            mg_st<D, NS>(slot(S_RHO), rho);
+            const double D1 = mg_sum_d((double)mg_dot<D, NS>(rho, mg_ld<D, NS>(slot(S_LP)), lane));
+            const double D2 = mg_sum_d((double)mg_dot<D, NS>(rho, mg_ld<D, NS>(slot(S_RP)), lane));
             if (forward) r_lp = lqv; else l_lp = lqv;
             cont = alive && (D1 >= 0.0) && (D2 >= 0.0);
             depth += 1;
@@ -769,13 +854,13 @@ __global__ void __launch_bounds__(128, D == 1 ? 4 : (D <= 2 ? 3 : 2)) nuts_mg_ke
         ad.dual(fmin(lar, 0.0), a.num_adapt, (T)a.target_accept);
         const int r = t - a.num_burnin;
         if (r >= 0 && a.store_draws) {
-            scatter(draws + (size_t)r * P, mg_ld<D>(slot(S_CQ)));
+            mp.scatter(draws + (size_t)r * P, mg_ld<D, NS>(slot(S_CQ)), lane);
             if (lane == 0)
                 write_stats<T>(stats + (size_t)r * SCCODA_NSTAT, lp_cur, lar, is_acc, eps, !not_div, leapfrogs, c_energy, cont);
         }
     }
     __syncwarp();
-    scatter(vec, mg_ld<D>(slot(S_CQ)));
+    mp.scatter(vec, mg_ld<D, NS>(slot(S_CQ)), lane);
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
 }

@@ -17,7 +17,7 @@ int select_kind(const KArgs& a, int kind, int dtype, int W) {
         a.dm.D == 1 && a.Umax == 2 && a.dm.K <= 31)
         return kind == KIND_HMC ? KIND_HMC_CC : KIND_NUTS_CC;
     if ((kind == KIND_HMC || kind == KIND_NUTS) && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 &&
-        a.dm.D <= kMgMaxD && a.Umax <= kMgMaxGroups && a.dm.K <= 31)
+        a.Umax <= kMgMaxGroups && (a.dm.K <= 31 ? a.dm.D <= kMgMaxD : (a.dm.K <= kMgMaxK && a.dm.D <= kMgMaxD2)))
         return kind == KIND_HMC ? KIND_HMC_MG : KIND_NUTS_MG;
     return kind;
 }
@@ -29,7 +29,7 @@ size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int d
         return cp.data_total + (size_t)chains_per_cta * cp.chain_total;
     }
     if (kind == KIND_HMC_MG || kind == KIND_NUTS_MG) {
-        const MgPlan mp = plan_mg(a.dm.N, a.dm.K, a.dm.D, (a.Umax + 1) / 2, a.NT, a.NOT,
+        const MgPlan mp = plan_mg(a.dm.N, a.dm.K, a.dm.D, (a.Umax + 1) / 2, a.dm.K <= 31 ? 1 : 2, a.NT, a.NOT,
                                   kind == KIND_NUTS_MG ? 11 + 2 * (a.max_depth + 1) : 0);
         return mp.data_total + (size_t)chains_per_cta * mp.chain_total;
     }

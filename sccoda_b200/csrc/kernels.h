@@ -136,32 +136,36 @@ __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT, int n_s
     return p;
 }
 
-// Shared-memory plan of the multi-group HMC kernel (hmc_mg.cuh): the arrays of CcPlan, one block per PAIR of groups
-// (UP = pairs of groups of the fullest dataset), plus the covariate values and row counts of the groups.
+// Shared-memory plan of the multi-group kernels (hmc_mg.cuh): the arrays of CcPlan, one block per (PAIR of groups,
+// column slot) — UP = pairs of groups of the fullest dataset, NS = cell types per lane (1: K <= 31, 2: K <= 62) —
+// plus the covariate values and row counts of the groups.
 struct MgPlan {
     size_t cf, yv, ov, rows, el, xg, cnt, bounds, red, data_total;   // per CTA
     size_t pc, vec, slots, chain_total;                               // per chain (relative)
 };
-constexpr int kMgMaxGroups = 16, kMgMaxD = 4;
-// n_slots: stored vectors of the NUTS tree (D float4 per lane each; 0 for HMC)
-__host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NT, int NOT, int n_slots) {
+constexpr int kMgMaxGroups = 16, kMgMaxD = 4, kMgMaxK = 62, kMgMaxD2 = 3 /* largest D with two cell types per lane */;
+// float4 per lane of one stored state vector: NS (alpha + D b_offset + D ind_raw) + D sigma
+__host__ __device__ constexpr int mg_vec_quads(int D, int NS) { return (NS * (1 + 2 * D) + D + 3) / 4; }
+// n_slots: stored vectors of the NUTS tree (0 for HMC)
+__host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NS, int NT, int NOT, int n_slots) {
     MgPlan p;
+    const size_t Q = (size_t)UP * NS;
     size_t o = 0;
-    p.cf = o; o += (size_t)UP * 6 * 32 * 8;                      // f32x2[UP][6][32] rational coefficients
-    p.yv = o; o += (size_t)UP * NT * kItemR * 32 * 8;            // f32x2[UP][NT][R][32] item counts
-    p.ov = o; o += (size_t)UP * NOT * 32 * 8;                    // f32x2[UP][NOT][32] odd counts
+    p.cf = o; o += Q * 6 * 32 * 8;                               // f32x2[UP][NS][6][32] rational coefficients
+    p.yv = o; o += Q * NT * kItemR * 32 * 8;                     // f32x2[UP][NS][NT][R][32] item counts
+    p.ov = o; o += Q * NOT * 32 * 8;                             // f32x2[UP][NS][NOT][32] odd counts
     p.rows = o; o += (size_t)N * 16;                             // (row total, host-like constant, slot of S_u, -)
     p.el = o; o += (size_t)N * K * 16;                           // (count, host constant, concentration slot, 1/count)
     p.xg = o; o += rnd16((size_t)UP * D * 8);                    // f32x2[UP][D] covariate values of the groups
     p.cnt = o; o += rnd16((size_t)UP * 2 * 4);                   // float[2 UP] rows per group
-    p.bounds = o; o += rnd16((size_t)(2 * UP + 1) * 4);          // int: items / odd counts per group pair, big elements
+    p.bounds = o; o += rnd16((size_t)(2 * Q + 1) * 4);           // int: items / odd counts per (group pair, slot), big elements
     p.red = o; o += 32;                                          // double[4]: staging reduction
     p.data_total = o;
     const size_t P = (size_t)D + 2 * (size_t)D * (K - 1) + K;
-    p.pc = 0;                                                    // float[2 UP][32] concentrations, slot u*32 + column
-    p.vec = (size_t)UP * 256;                                    // flat state vector
-    p.slots = p.vec + rnd16(P * 4);                              // float4[n_slots][D][32]
-    p.chain_total = p.slots + (size_t)n_slots * D * 512;
+    p.pc = 0;                                                    // float[2 UP][32 NS] concentrations, slot u*32*NS + column
+    p.vec = Q * 256;                                             // flat state vector
+    p.slots = p.vec + rnd16(P * 4);                              // float4[n_slots][quads][32]
+    p.chain_total = p.slots + (size_t)n_slots * mg_vec_quads(D, NS) * 512;
     return p;
 }
 

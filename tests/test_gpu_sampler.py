@@ -209,13 +209,62 @@ def test_case_control_kernel_cell_type_range(K):
     _cc_vs_oracle(xs, ys, [K - 1, 0])
 
 
-def test_case_control_kernel_k32_falls_back_to_generic():
+def test_case_control_kernel_k32_takes_the_two_columns_per_lane_kernel():
+    """K = 32 no longer fits one cell type per lane plus the row totals: the multi-group kernel with two columns per lane
+    takes it (K <= 62), beyond that the generic kernel."""
     from sccoda_b200.engine import DeviceProblem
     x, y = synthetic_dataset(3, N=10, K=32)
     prob = DeviceProblem.from_arrays(x, y, 31, chains=2, dtype=np.float32, grouped=True)
     out = prob.sample(_init(np.random.RandomState(0), 1, 32, 2)[None] * 0.5,
                       prob.make_sampler(0, 6, 0, num_adapt=6, seed=1, warps_per_chain=1))
+    assert out.kernel_kind == 5 and np.isfinite(out.draws.cpu().numpy()).all()
+    x, y = synthetic_dataset(3, N=10, K=63)
+    prob = DeviceProblem.from_arrays(x, y, 31, chains=2, dtype=np.float32, grouped=True)
+    out = prob.sample(_init(np.random.RandomState(0), 1, 63, 2)[None] * 0.5,
+                      prob.make_sampler(0, 6, 0, num_adapt=6, seed=1, warps_per_chain=1))
     assert out.kernel_kind == 1 and np.isfinite(out.draws.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("method", [0, 2])
+@pytest.mark.parametrize("K,kind", [(32, "case_control"), (45, "case_control"), (62, "case_control"), (40, "conditions4"),
+                                    (33, "factorial2x2"), (50, "levels3")])
+def test_two_columns_per_lane_kernels_follow_generic_kernel(K, kind, method):
+    """32 <= K <= 62: a lane owns the cell types l and 32 + l (hmc_mg.cuh, NS = 2).  Same checks as for K <= 31: the
+    oracle's log-density at the traced states, the generic kernel's first transitions, bit-identical chunked resume."""
+    from oracle import np_oracle as o
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    B, C, steps = 2, 2, 8
+    if kind == "case_control":
+        xs, ys = zip(*[synthetic_dataset(140 + b, N=14, K=K) for b in range(B)])
+        ys = list(ys)
+        ys[1][2, K - 3] = 0.0                                   # a pseudocount dataset
+    else:
+        xs, ys = zip(*[_multi_group_dataset(150 + b, kind, N=24, K=K, zero_frac=0.1 * (b == 1)) for b in range(B)])
+    D = xs[0].shape[1]
+    refs = [K - 1, 5]
+    pk = pack(np.stack(xs), np.stack(ys), np.asarray(refs), dtype=np.float32)
+    assert pk.grouped == 1
+    prob = DeviceProblem(pk, chains=C)
+    init = _init(np.random.RandomState(7), D, K, B * C).reshape(B, C, -1) * 0.4
+    init[..., :D] = 1.0
+    kw = dict(num_adapt=steps, seed=4, warps_per_chain=1, max_tree_depth=5)
+    outs = [prob.sample(init, prob.make_sampler(method, steps, 0, generic_only=g, **kw)) for g in (True, False)]
+    assert outs[0].kernel_kind == (1 if method == 0 else 2) and outs[1].kernel_kind == (5 if method == 0 else 6)
+    d = outs[1].draws.double().cpu().numpy()
+    lp = outs[1].stat("target_log_prob").double().cpu().numpy()
+    assert np.isfinite(d).all() and np.isfinite(lp).all()
+    for b in range(B):
+        m = o.prepare(xs[b], ys[b], int(refs[b]))
+        for c in range(C):
+            want = np.array([o.logp(d[b, c, i], m) for i in range(steps)])
+            assert np.abs(lp[b, c] - want).max() < 5e-6 * np.abs(want).max() + 4e-3, (b, c, np.abs(lp[b, c] - want).max())
+    n = 3
+    assert np.abs(outs[0].draws.cpu().numpy()[:, :, :n] - outs[1].draws.cpu().numpy()[:, :, :n]).max() < 5e-3
+    for name in ("is_accepted", "leapfrogs_taken"):
+        assert np.array_equal(outs[0].stat(name).cpu().numpy()[:, :, :n], outs[1].stat(name).cpu().numpy()[:, :, :n]), name
+    many = prob.sample(init, prob.make_sampler(method, steps, 0, **kw), chunk=3)
+    assert many.launches > 1 and np.array_equal(many.draws.cpu().numpy(), outs[1].draws.cpu().numpy())
 
 
 def test_case_control_kernel_ragged_batches():
