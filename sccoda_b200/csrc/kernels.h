@@ -10,7 +10,7 @@ namespace sccoda {
 enum {
     KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2,
     KIND_HMC_CC = 3, KIND_NUTS_CC = 4,   // case/control specialisations (hmc_cc.cuh)
-    KIND_HMC_MG = 5, KIND_NUTS_MG = 6    // up to 16 covariate groups, D <= 4 on the same lane-per-cell-type layout (hmc_mg.cuh)
+    KIND_HMC_MG = 5, KIND_NUTS_MG = 6    // up to 16 covariate groups, D <= 4, K <= 62 on the same lane-per-cell-type layout (hmc_mg.cuh)
 };
 
 }  // namespace sccoda
