@@ -192,7 +192,7 @@ int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, in
 
 /* Which kernel sccoda_sample would launch: 1 = generic HMC, 2 = generic NUTS, 3 / 4 = the case/control HMC / NUTS
  * specialisations (D == 1, Umax == 2 covariate groups, K <= 31, fp32, one warp per chain, grouped layout), 5 = the
- * multi-group HMC kernel (same layout, up to 16 covariate groups; D <= 4 with K <= 31, D <= 3 with two cell types
+ * multi-group HMC kernel (same layout, up to 32 covariate groups; D <= 4 with K <= 31, D <= 3 with two cell types
  * per lane for K <= 62). */
 int sccoda_kernel_kind(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* kind);
 

@@ -195,7 +195,7 @@ def _no_items(B: int, K: int, Umax: int) -> dict:
 def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) -> PackedProblem:
     """x: [B,N,D] or [N,D]; y: [B,N,K] or [N,K]; ref: int or [B].
 
-    grouped: None = choose (pair/item gradient path for the designs the lane-per-cell-type kernels take — at most 16
+    grouped: None = choose (pair/item gradient path for the designs the lane-per-cell-type kernels take — at most 32
     covariate groups, D <= 4 and K <= 31 or D <= 3 and K <= 62 —
     and whenever the covariate groups are large enough that the item padding stays below 60 % of the counts — unless
     the pair/item arrays of the dataset would not fit one CTA's shared memory), True / False = force."""
@@ -279,7 +279,7 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
         # designs with few covariate groups (case/control, a handful of conditions, small factorials) always take the
         # pair/item layout: the lane-per-cell-type kernels (hmc_cc.cuh, hmc_mg.cuh) evaluate a padded item as cheaply
         # as a full one; otherwise only when the item padding stays below 60 % of the counts
-        lane_owned = Umax <= 16 and ((K <= 31 and D <= 4) or (K <= 62 and D <= 3))
+        lane_owned = Umax <= 32 and ((K <= 31 and D <= 4) or (K <= 62 and D <= 3))
         grouped = bool(lane_owned or ITEM_R * int(it["NI"].max()) <= 1.6 * N * (K + 1))
     if grouped:
         # The pair/item gradient does not walk the element list; only the value pass does, and it does not care

@@ -105,9 +105,12 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, i
         kind = kind_in;
         if (attempt == 1) a.generic_only = 1;
         int W = W_req;
-        if (W == 0 && sccoda::select_kind(a, kind, p->dtype, 1) != kind && (p->NT <= 8 || p->B * p->C >= 148 * 8)) {
+        if (W == 0 && sccoda::select_kind(a, kind, p->dtype, 1) != kind &&
+            (p->B * p->C >= 148 * 8 || (p->NT <= 8 && p->Umax <= 16))) {
             // case/control and multi-group shapes: the lane-per-cell-type kernels (one warp per chain) unless a few
             // chains face very long groups (more than 40 rows per group: the items of a pair are walked by one lane)
+            // or very many groups (the group pairs are walked by one warp): the generic kernels spread those over
+            // several warps per chain, which wins while the device is not full
             W = 1;
         }
         if (W == 0) {

@@ -1,5 +1,6 @@
 // K2mg — HMC on the lane-per-cell-type layout of hmc_cc.cuh for designs with MORE than two covariate groups:
-// up to 16 groups (distinct rows of the design matrix: a few conditions, 2x2 ... 2x2x2x2 factorials), D <= 4
+// up to 32 groups (distinct rows of the design matrix: a few conditions, 2x2 ... 2x2x2x2 factorials, a continuous
+// covariate on a few dozen samples), D <= 4
 // covariates, fp32, one warp per chain; K <= 31 cell types with one cell type per lane (NS = 1), K <= 62 with two
 // (NS = 2: lane l owns the columns l and 32 + l; the row totals are column K).
 //

@@ -10,7 +10,7 @@ namespace sccoda {
 enum {
     KIND_LOGP = 0, KIND_HMC = 1, KIND_NUTS = 2,
     KIND_HMC_CC = 3, KIND_NUTS_CC = 4,   // case/control specialisations (hmc_cc.cuh)
-    KIND_HMC_MG = 5, KIND_NUTS_MG = 6    // up to 16 covariate groups, D <= 4, K <= 62 on the same lane-per-cell-type layout (hmc_mg.cuh)
+    KIND_HMC_MG = 5, KIND_NUTS_MG = 6    // up to 32 covariate groups, D <= 4, K <= 62 on the same lane-per-cell-type layout (hmc_mg.cuh)
 };
 
 }  // namespace sccoda
@@ -143,7 +143,7 @@ struct MgPlan {
     size_t cf, yv, ov, rows, el, xg, cnt, bounds, red, data_total;   // per CTA
     size_t pc, vec, slots, chain_total;                               // per chain (relative)
 };
-constexpr int kMgMaxGroups = 16, kMgMaxD = 4, kMgMaxK = 62, kMgMaxD2 = 3 /* largest D with two cell types per lane */;
+constexpr int kMgMaxGroups = 32, kMgMaxD = 4, kMgMaxK = 62, kMgMaxD2 = 3 /* largest D with two cell types per lane */;
 // float4 per lane of one stored state vector: NS (alpha + D b_offset + D ind_raw) + D sigma
 __host__ __device__ constexpr int mg_vec_quads(int D, int NS) { return (NS * (1 + 2 * D) + D + 3) / 4; }
 // n_slots: stored vectors of the NUTS tree (0 for HMC)

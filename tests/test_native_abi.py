@@ -89,6 +89,41 @@ def test_launch_plan_scales_warps_for_few_chains_and_big_models():
     assert rc == 0 and w == 2
 
 
+def test_kernel_dispatch_table():
+    """Which kernel the library picks (sccoda_kernel_kind): case/control, multi-group (one or two cell types per
+    lane), generic."""
+    def kinds(x, y, ref, C=4096):
+        pk = pack(x, y, ref)
+        out = []
+        for method in (0, 2):
+            k = ctypes.c_int32()
+            assert nat.lib().sccoda_kernel_kind(ctypes.byref(_problem(pk, C)), ctypes.byref(_sampler(method=method)),
+                                                ctypes.byref(k)) == 0
+            out.append(k.value)
+        return tuple(out)
+
+    rs = np.random.RandomState(0)
+    x, y = synthetic_dataset(0, N=12, K=20)
+    assert kinds(x, y, 19) == (3, 4)                                        # case/control, K <= 31
+    x, y = synthetic_dataset(0, N=12, K=40)
+    assert kinds(x, y, 39) == (5, 6)                                        # case/control, 32 <= K <= 62: two columns per lane
+    x, y = synthetic_dataset(0, N=12, K=63)
+    assert kinds(x, y, 62) == (1, 2)                                        # K > 62: generic
+    x4 = ((np.arange(32)[:, None] >> np.arange(4)[None, :]) & 1).astype(float)
+    _, y = synthetic_dataset(0, N=32, K=20)
+    assert kinds(x4, y, 19) == (5, 6)                                       # 2^4 factorial: D = 4, 16 groups
+    _, y = synthetic_dataset(0, N=32, K=40)
+    assert kinds(x4, y, 39) == (1, 2)                                       # D = 4 with K > 31: generic
+    assert kinds(x4[:, :3], y, 39) == (5, 6)                                # D = 3 with K <= 62
+    x5 = ((np.arange(64)[:, None] >> np.arange(5)[None, :]) & 1).astype(float)
+    _, y = synthetic_dataset(0, N=64, K=20)
+    assert kinds(x5, y, 19) == (1, 2)                                       # 32 groups / D = 5: generic
+    _, y = synthetic_dataset(0, N=12, K=20)
+    assert kinds(rs.randn(12, 1), y, 19) == (5, 6)                          # continuous covariate, 12 rows = 12 groups
+    _, y = synthetic_dataset(0, N=40, K=20)
+    assert kinds(rs.randn(40, 1), y, 19) == (1, 2)                          # ... 40 groups: generic
+
+
 def test_launch_plan_falls_back_when_the_specialised_tile_does_not_fit():
     """Long case/control datasets: the lane-per-cell-type kernels stage the whole element list (16 B per count) in
     shared memory; when that does not fit, the planner takes the generic kernels instead of failing, and the packer

@@ -153,12 +153,15 @@ def test_pair_item_layout_reproduces_brackets(shape):
 
 
 def test_pair_item_layout_auto_mode():
-    """Few covariate groups -> grouped gradient path; one row per group (continuous covariate) -> element path."""
+    """Few covariate groups -> grouped gradient path (also a continuous covariate on a few dozen rows: the
+    lane-per-cell-type kernels take up to 32 groups); one row per group beyond that -> element path."""
     x, y = synthetic_dataset(0)
     assert pack(x, y, 19).grouped == 1
     rs = np.random.RandomState(0)
-    assert pack(x + rs.randn(*x.shape), y, 19).grouped == 0
-    assert pack(x + rs.randn(*x.shape), y, 19, grouped=True).grouped == 1
+    assert pack(x + rs.randn(*x.shape), y, 19).grouped == 1
+    x40, y40 = synthetic_dataset(0, N=40)
+    assert pack(x40 + rs.randn(*x40.shape), y40, 19).grouped == 0
+    assert pack(x40 + rs.randn(*x40.shape), y40, 19, grouped=True).grouped == 1
     # items of a batch are padded to a common even count; unused item slots are harmless (count 6, pair 0)
     xs, ys = zip(*[synthetic_dataset(s) for s in range(4)])
     ys = np.stack(ys)
