@@ -122,6 +122,10 @@ def test_kernel_dispatch_table():
     assert kinds(rs.randn(12, 1), y, 19) == (5, 6)                          # continuous covariate, 12 rows = 12 groups
     _, y = synthetic_dataset(0, N=40, K=20)
     assert kinds(rs.randn(40, 1), y, 19) == (1, 2)                          # ... 40 groups: generic
+    _, y = synthetic_dataset(0, N=24, K=20)
+    xc = rs.randn(24, 1)
+    assert kinds(xc, y, 19) == (5, 6)                                       # 24 groups, a full device: one warp per chain
+    assert kinds(xc, y, 19, C=4) == (1, 2)                                  # ... a handful of chains: several warps per chain
 
 
 def test_launch_plan_falls_back_when_the_specialised_tile_does_not_fit():
