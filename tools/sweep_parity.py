@@ -20,16 +20,38 @@ ap.add_argument("--chains", type=int, default=4)
 ap.add_argument("--K", type=int, default=20)
 ap.add_argument("--results", type=int, default=20000)
 ap.add_argument("--burnin", type=int, default=5000)
+ap.add_argument("--conditions", type=int, default=2, help="> 2: one-hot coded conditions (D = conditions - 1), 5 rows each, "
+                                                             "one true effect per condition")
 a = ap.parse_args()
 B, C, K, nr, nb = a.datasets, a.chains, a.K, a.results, a.burnin
 
-x, y, w_true = generate_sweep(B, K=K, n_per_group=10)
+if a.conditions > 2:
+    D, N = a.conditions - 1, 5 * a.conditions
+    lv = np.arange(N) % a.conditions
+    x1 = (lv[:, None] == np.arange(1, a.conditions)[None, :]).astype(float)
+    x = np.broadcast_to(x1, (B, N, D)).copy()
+    y = np.zeros((B, N, K))
+    w_true = np.zeros((B, D, K))
+    for i in range(B):
+        rs = np.random.RandomState(4321 + i)
+        b0 = rs.uniform(-3, 3, size=K)
+        for d in range(D):
+            w_true[i, d, rs.randint(K - 1)] = rs.choice([0.5, 1.0, 1.5])
+        logits = b0[None, :] + x1 @ w_true[i] + np.sqrt(0.05) * rs.randn(N, K)
+        pr = np.exp(logits - logits.max(axis=1, keepdims=True))
+        pr /= pr.sum(axis=1, keepdims=True)
+        for n in range(N):
+            y[i, n] = rs.multinomial(5000, pr[n])
+else:
+    D = 1
+    x, y, w1 = generate_sweep(B, K=K, n_per_group=10)
+    w_true = w1[:, None, :]
 cfg = sch.SweepConfig(method=0, num_results=nr, num_burnin=nb, chains=C, seed=11)
 t0 = time.time()
 res, shard = sch.run_sweep(x, y, K - 1, cfg)
 t_dev = time.time() - t0
 ms = [o.prepare(x[b], y[b], K - 1) for b in range(B)]
-init = sch.initial_states(B, C, 1, K, seed=5)
+init = sch.initial_states(B, C, D, K, seed=5)
 t0 = time.time()
 d, st_o = c_oracle.sample(np.stack([m.x for m in ms]), np.stack([m.y for m in ms]), np.stack([m.n_total for m in ms]),
                           [m.logp_const for m in ms], [m.ref for m in ms], init, 0, nr, nb, seed=99)
@@ -38,41 +60,47 @@ used = d[:, :, nb:, :]
 lp_o = st_o["target_log_prob"][:, :, nb:]
 sane = lp_o.max(axis=2) < np.median(lp_o, axis=(1, 2))[:, None] + 500.0       # oracle chains outside the precision-loss mode
 keep = sane.sum(1) >= 2
-sig, boff, iraw = used[..., 0:1], used[..., 1:K], used[..., K:2 * K - 1]
+K1 = K - 1
+sig = used[..., :D, None]                                                      # [B,C,S,D,1]
+boff = used[..., D:D + D * K1].reshape(used.shape[:3] + (D, K1))
+iraw = used[..., D + D * K1:D + 2 * D * K1].reshape(used.shape[:3] + (D, K1))
 with np.errstate(over="ignore"):
-    beta = 1.0 / (1.0 + np.exp(-50.0 * iraw)) * sig * boff
+    beta = 1.0 / (1.0 + np.exp(-50.0 * iraw)) * sig * boff                     # [B,C,S,D,K-1]; the reference column is last
 nzm = np.abs(beta) > 1e-3
-inc_chain = nzm.mean(2)
-wgt = sane[:, :, None] / np.maximum(sane.sum(1), 1)[:, None, None]
-inc_o = np.concatenate([(inc_chain * wgt).sum(1), np.zeros((B, 1))], axis=1)
-nz = (np.where(nzm, beta, 0.0).sum(2) * sane[:, :, None]).sum(1) / np.maximum((nzm.sum(2) * sane[:, :, None]).sum(1), 1)
-nz_o = np.concatenate([nz, np.zeros((B, 1))], axis=1)
+inc_chain = nzm.mean(2)                                                        # [B,C,D,K-1]
+w4 = sane[:, :, None, None]
+wgt = w4 / np.maximum(sane.sum(1), 1)[:, None, None, None]
+pad = np.zeros((B, D, 1))
+inc_o = np.concatenate([(inc_chain * wgt).sum(1), pad], axis=2).reshape(B, D * K)
+nz = (np.where(nzm, beta, 0.0).sum(2) * w4).sum(1) / np.maximum((nzm.sum(2) * w4).sum(1), 1)
+nz_o = np.concatenate([nz, pad], axis=2).reshape(B, D * K)
 inc_d = res["inclusion_prob"]
 mean_c = (inc_chain * wgt).sum(1, keepdims=True)
-var_c = (((inc_chain - mean_c) ** 2) * sane[:, :, None]).sum(1) / np.maximum(sane.sum(1)[:, None] - 1, 1)
-se = float(np.sqrt(np.mean((var_c / np.maximum(sane.sum(1), 1)[:, None])[keep])))
-diff = (inc_d - inc_o)[keep][:, :K - 1]
+var_c = (((inc_chain - mean_c) ** 2) * w4).sum(1) / np.maximum(sane.sum(1)[:, None, None] - 1, 1)
+se = float(np.sqrt(np.mean((var_c / np.maximum(sane.sum(1), 1)[:, None, None])[keep])))
+nonref = (np.arange(D * K) % K) != K - 1
+diff = (inc_d - inc_o)[keep][:, nonref]
 thr_o, final_o = sch.credible_effect_calls(inc_o, nz_o, 0.05)
 call_d, call_o = (res["final_effect"] != 0)[keep], (final_o != 0)[keep]
-kt = np.argmax(w_true, axis=1)[keep]
-rows = np.arange(int(keep.sum()))
-strong = w_true[keep][rows, kt] >= 1.0
+wt = w_true.reshape(B, D * K)[keep]
+true_mask = wt != 0
+strong_mask = wt >= 1.0
 out = {
-    "workload": f"{B} datasets x {C} chains, K=N={K}, sample_hmc({nr},{nb}), L=10; device fp32 (kernel kind {shard.out.kernel_kind}) vs C oracle fp64, independent streams",
+    "workload": f"{B} datasets x {C} chains, K={K}, N={y.shape[1]}, D={D}, sample_hmc({nr},{nb}), L=10; device fp32 (kernel kind {shard.out.kernel_kind}) vs C oracle fp64, independent streams",
     "device_wall_s": t_dev, "device_kernel_ms": shard.out.kernel_ms, "oracle_wall_s": t_orc,
     "oracle_chains_in_precision_loss_mode": float(1.0 - sane.mean()), "datasets_compared": int(keep.sum()),
     "entries": int(diff.size), "typical_standard_error_of_an_entry": se,
     "inclusion_prob_rms_diff": float(np.sqrt(np.mean(diff ** 2))), "inclusion_prob_max_abs_diff": float(np.abs(diff).max()),
     "inclusion_prob_mean_diff": float(diff.mean()),
-    "inclusion_prob_correlation": float(np.corrcoef(inc_d[keep][:, :K - 1].ravel(), inc_o[keep][:, :K - 1].ravel())[0, 1]),
+    "inclusion_prob_correlation": float(np.corrcoef(inc_d[keep][:, nonref].ravel(), inc_o[keep][:, nonref].ravel())[0, 1]),
     "credible_call_disagreement_rate": float((call_d != call_o).mean()),
     "credible_calls_device": int(call_d.sum()), "credible_calls_oracle": int(call_o.sum()),
-    "true_effect_called_device": float(call_d[rows, kt].mean()), "true_effect_called_oracle": float(call_o[rows, kt].mean()),
-    "true_effect_called_device_strong": float(call_d[rows, kt][strong].mean()) if strong.any() else None,
-    "true_effect_called_oracle_strong": float(call_o[rows, kt][strong].mean()) if strong.any() else None,
-    "true_effect_same_call": float((call_d[rows, kt] == call_o[rows, kt]).mean()),
-    "false_positive_rate_device": float((call_d.sum() - call_d[rows, kt].sum()) / (call_d.size - rows.size)),
-    "false_positive_rate_oracle": float((call_o.sum() - call_o[rows, kt].sum()) / (call_o.size - rows.size)),
+    "true_effect_called_device": float(call_d[true_mask].mean()), "true_effect_called_oracle": float(call_o[true_mask].mean()),
+    "true_effect_called_device_strong": float(call_d[strong_mask].mean()) if strong_mask.any() else None,
+    "true_effect_called_oracle_strong": float(call_o[strong_mask].mean()) if strong_mask.any() else None,
+    "true_effect_same_call": float((call_d[true_mask] == call_o[true_mask]).mean()),
+    "false_positive_rate_device": float(call_d[~true_mask & nonref[None, :]].mean()),
+    "false_positive_rate_oracle": float(call_o[~true_mask & nonref[None, :]].mean()),
     "acc_rate_device": float(np.mean(res["acc_rate"])) if "acc_rate" in res else None,
     "acc_rate_oracle_sane_chains": float(st_o["is_accepted"][sane].mean()),
     "final_step_size_oracle_sane_chains": float(st_o["step_size"][:, :, -1][sane].mean()),
