@@ -138,27 +138,26 @@ __device__ __forceinline__ float pair_bracket<float>(float rat, const float* __r
 // Gradient of the log-density at theta, grouped form.  Same contract as dm_grad (model.cuh): every component is
 // handed once to epi(i, value) by its owner, a trailing group sync publishes what the epilogue wrote, and the
 // scratch keeps the concentrations (PairRec::c, pairs u*K + k and Umax*K + u) for dm_value.
-template <typename T, int W, class Epi>
-__device__ __forceinline__ void dm_grad_items(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
-                                              uint32_t theta_off, const Group<W>& g, const Epi& epi) {
+//
+// The pass comes in two halves so that a caller can run the second half and the value pass side by side on two halves
+// of the chain's warps (they only share read access to the pair records): `front` = effects and pair records (P0, P1),
+// `back` = items, brackets and the chain rule (E, P2, C).
+template <typename T, int W>
+__device__ __forceinline__ void dm_grad_items_front(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                                    uint32_t theta_off, const Group<W>& g) {
     const int tid = g.tid;
     constexpr int TS = Group<W>::SIZE;
-    constexpr int R = SCCODA_ITEM_R;
-    const int K = dm.K, D = dm.D, K1 = dm.K1, DK1 = dm.DK1, U = dt.U, ref = dt.ref, tot0 = dt.tot0, NF = dt.NF;
+    const int K = dm.K, D = dm.D, K1 = dm.K1, DK1 = dm.DK1, U = dt.U, ref = dt.ref, tot0 = dt.tot0;
     const T* sigma = sp<T>(theta_off);
     const T* boff = sigma + D;
     const T* iraw = boff + DK1;
     const T* alpha = iraw + DK1;
     PairRec<T>* prec = sp<PairRec<T>>(cs.cp);
-    T* A = sp<T>(cs.G);          // result slots [NP*NF + 1]
     T* Ssm = sp<T>(cs.Gu);
     T* beta = sp<T>(cs.beta);
     T* ind = sp<T>(cs.ind);
     const T* xu = sp<T>(dt.xu);
     const T* pcoef = sp<T>(dt.pcoef);
-    const T* iy = sp<T>(dt.iy);
-    const uint16_t* ipair = sp<uint16_t>(dt.ipair);
-    const uint16_t* ipos = sp<uint16_t>(dt.ipos);
     const int lane = tid & 31, warp = tid >> 5;
 
     // ---- P0: spike-and-slab effects, one column per thread                                        (:724-734)
@@ -222,6 +221,26 @@ __device__ __forceinline__ void dm_grad_items(const Dims& dm, const DataTile<T>&
         for (int u = tid; u < U; u += TS) prec[tot0 + u] = make_rec(Ssm[u], pcoef + 6 * (tot0 + u));
     }
     g.sync();
+}
+
+template <typename T, int W, class Epi>
+__device__ __forceinline__ void dm_grad_items_back(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                                   uint32_t theta_off, const Group<W>& g, const Epi& epi) {
+    const int tid = g.tid;
+    constexpr int TS = Group<W>::SIZE;
+    constexpr int R = SCCODA_ITEM_R;
+    const int K = dm.K, D = dm.D, K1 = dm.K1, DK1 = dm.DK1, U = dt.U, ref = dt.ref, tot0 = dt.tot0, NF = dt.NF;
+    const T* sigma = sp<T>(theta_off);
+    const T* boff = sigma + D;
+    const T* iraw = boff + DK1;
+    const T* alpha = iraw + DK1;
+    PairRec<T>* prec = sp<PairRec<T>>(cs.cp);
+    T* A = sp<T>(cs.G);          // result slots [NP*NF + 1]
+    const T* ind = sp<T>(cs.ind);
+    const T* xu = sp<T>(dt.xu);
+    const T* iy = sp<T>(dt.iy);
+    const uint16_t* ipair = sp<uint16_t>(dt.ipair);
+    const uint16_t* ipos = sp<uint16_t>(dt.ipos);
     // ---- E: items (one per thread and pass) and odd groups (rare), each into its own result slot
     {
         const int NIs = dt.NImax;
@@ -313,6 +332,13 @@ __device__ __forceinline__ void dm_grad_items(const Dims& dm, const DataTile<T>&
         }
     }
     g.sync();
+}
+
+template <typename T, int W, class Epi>
+__device__ __forceinline__ void dm_grad_items(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                              uint32_t theta_off, const Group<W>& g, const Epi& epi) {
+    dm_grad_items_front<T, W>(dm, dt, cs, theta_off, g);
+    dm_grad_items_back<T, W>(dm, dt, cs, theta_off, g, epi);
 }
 
 }  // namespace sccoda

@@ -171,6 +171,40 @@ __device__ __forceinline__ double value_of(const Dims& dm, const DataTile<T>& dt
     else return dm_value<T, W, CPsi<T>>(dm, dt, cs, theta_off, g);
 }
 
+// Gradient and value at the same state (a NUTS leaf).  With the pair / item layout and at least eight warps per chain
+// the second half of the gradient pass (items, brackets, chain rule) and the value pass run SIDE BY SIDE on the two
+// halves of the chain's warps: both only read the pair records the first half wrote, and a chain with many warps is
+// bound by the latency of its dependent instruction chains, not by issue slots (BASELINE config 3: 16 warps per
+// chain on one SM).  Each half synchronises on its own named barrier and reduces in its own half of the scratch.
+template <typename T, int W, bool GR, class Epi>
+__device__ __forceinline__ double grad_value_of(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                                uint32_t theta_off, const Group<W>& g, const Epi& epi) {
+    if constexpr (GR && W >= 8) {
+        constexpr int H = W / 2;
+        const FrozenEpi<T, Epi> fe{epi, dm};
+        dm_grad_items_front<T, W>(dm, dt, cs, theta_off, g);
+        Group<H> h;
+        const bool second = g.tid >= 32 * H;
+        h.tid = g.tid - (second ? 32 * H : 0);
+        h.gid = 8 + 2 * g.gid + (second ? 1 : 0);                  // named barriers 9.. (the chain groups use 1..4)
+        h.red = g.red + (second ? 8u * W : 0u);                    // the group's scratch is double[2 W]
+        double* out = sp<double>(cs.Gu);                           // free once the pair records are written
+        if (!second) {
+            dm_grad_items_back<T, H>(dm, dt, cs, theta_off, h, fe);
+        } else {
+            const double v = dm_value<T, H, PairRec<T>>(dm, dt, cs, theta_off, h);
+            if (h.tid == 0) *out = v;
+        }
+        g.sync();
+        const double v = *out;
+        g.sync();                                                  // `out` is reused by the next gradient's row sums
+        return v;
+    } else {
+        grad_of<T, W, GR>(dm, dt, cs, theta_off, g, epi);
+        return value_of<T, W, GR>(dm, dt, cs, theta_off, g);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 unit kernel: value + gradient at given states
 // ------------------------------------------------------------------------------------------------
@@ -523,8 +557,7 @@ __global__ void SCCODA_BOUNDS(W) nuts_kernel(const __grid_constant__ KArgs a) {
                     }
                 }
                 g.sync();
-                grad_of<T, W, GR>(a.dm, dt, cs, o_q, g, StoreGrad<T>{gq});
-                lqv = value_of<T, W, GR>(a.dm, dt, cs, o_q, g);
+                lqv = grad_value_of<T, W, GR>(a.dm, dt, cs, o_q, g, StoreGrad<T>{gq});
                 if (boot) break;
                 T kk = T(0);
 #pragma unroll 1

@@ -28,7 +28,7 @@ def _oracle_run(x, y, ref, init, method, nr, nb, **kw):
 
 
 @pytest.mark.parametrize("method,steps,tol", [(0, 40, 1e-9), (1, 8, 1e-7), (2, 6, 1e-6)])
-@pytest.mark.parametrize("W", [1, 2, 4])
+@pytest.mark.parametrize("W", [1, 2, 4, 8, 16])      # W >= 8 + grouped + NUTS: gradient and value side by side
 @pytest.mark.parametrize("grouped", [False, True])
 def test_fp64_trajectory_follows_oracle(method, steps, tol, W, grouped):
     from sccoda_b200.engine import DeviceProblem
