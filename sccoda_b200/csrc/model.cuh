@@ -137,9 +137,15 @@ struct Group {
             if ((tid & 31) == 0) r[tid >> 5] = v;
             sync();
             // second stage as a tree over the W warp sums (a serial walk costs W dependent shared-memory loads)
-            v = r[tid & (W - 1)];
+            if constexpr ((W & (W - 1)) == 0) {
+                v = r[tid & (W - 1)];
 #pragma unroll
-            for (int o = W >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                for (int o = W >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            } else {   // any number of warps (the split groups of grad_value_of): lanes >= W carry zeros
+                v = (tid & 31) < W ? r[tid & 31] : V(0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            }
         }
         return v;
     }
@@ -160,9 +166,16 @@ struct Group {
             sync();
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                V t = r[(tid & (W - 1)) * NV + j];
+                V t;
+                if constexpr ((W & (W - 1)) == 0) {
+                    t = r[(tid & (W - 1)) * NV + j];
 #pragma unroll
-                for (int o = W >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    for (int o = W >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                } else {
+                    t = (tid & 31) < W ? r[(tid & 31) * NV + j] : V(0);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                }
                 v[j] = t;
             }
         }
