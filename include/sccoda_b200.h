@@ -12,6 +12,8 @@
  *   sccoda_summarize      the per-draw post-processing of get_y_hat and CAResult.complete_beta_df
  *                                                                            sccoda/model/scCODA_model.py:800-834,
  *                                                                            sccoda/util/result_classes.py:240-258
+ *   sccoda_predict        the per-draw concentration / prediction arrays of get_y_hat, on demand
+ *                                                                            sccoda/model/scCODA_model.py:821-827
  *   sccoda_sample_host    the same sampling call with HOST buffers (what a Python/ctypes caller that owns
  *                         numpy arrays binds; copies host<->device inside)
  *
