@@ -171,33 +171,37 @@ __device__ __forceinline__ double value_of(const Dims& dm, const DataTile<T>& dt
     else return dm_value<T, W, CPsi<T>>(dm, dt, cs, theta_off, g);
 }
 
-// Gradient and value at the same state (a NUTS leaf).  With the pair / item layout and at least eight warps per chain
-// the second half of the gradient pass (items, brackets, chain rule) and the value pass run SIDE BY SIDE on the two
-// parts of the chain's warps: both only read the pair records the first half wrote, and a chain with many warps is
+// Gradient and value at the same state (a NUTS leaf).  With at least eight warps per chain the second half of the
+// gradient pass (items / elements, brackets or column sums, chain rule) and the value pass run SIDE BY SIDE on two
+// parts of the chain's warps: both only read what the first half wrote, and a chain with many warps is
 // bound by the latency of its dependent instruction chains, not by issue slots (BASELINE config 3: 16 warps per
 // chain on one SM).  Each half synchronises on its own named barrier and reduces in its own half of the scratch.
 template <typename T, int W, bool GR, class Epi>
 __device__ __forceinline__ double grad_value_of(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
                                                 uint32_t theta_off, const Group<W>& g, const Epi& epi) {
-    if constexpr (GR && W >= 8) {
+    if constexpr (W >= 8) {
         // the value pass is the longer of the two: it gets 5/8 of the warps
         constexpr int HB = (3 * W) / 8, HV = W - HB;
         const FrozenEpi<T, Epi> fe{epi, dm};
-        dm_grad_items_front<T, W>(dm, dt, cs, theta_off, g);
+        if constexpr (GR) dm_grad_items_front<T, W>(dm, dt, cs, theta_off, g);
+        else dm_grad_front<T, W>(dm, dt, cs, theta_off, g);
         const bool second = g.tid >= 32 * HB;
-        double* out = sp<double>(cs.Gu);                           // free once the pair records are written
+        double* out = sp<double>(cs.Gu);                           // free once the front half is done
         if (!second) {
             Group<HB> h;
             h.tid = g.tid;
             h.gid = 8 + 2 * g.gid;                                 // named barriers 9, 10 (the chain groups use 1..4)
             h.red = g.red;                                         // the group's scratch is double[2 W]
-            dm_grad_items_back<T, HB>(dm, dt, cs, theta_off, h, fe);
+            if constexpr (GR) dm_grad_items_back<T, HB>(dm, dt, cs, theta_off, h, fe);
+            else dm_grad_back<T, HB>(dm, dt, cs, theta_off, h, fe);
         } else {
             Group<HV> h;
             h.tid = g.tid - 32 * HB;
             h.gid = 9 + 2 * g.gid;
             h.red = g.red + 16u * HB;
-            const double v = dm_value<T, HV, PairRec<T>>(dm, dt, cs, theta_off, h);
+            double v;
+            if constexpr (GR) v = dm_value<T, HV, PairRec<T>>(dm, dt, cs, theta_off, h);
+            else v = dm_value<T, HV, CPsi<T>>(dm, dt, cs, theta_off, h);
             if (h.tid == 0) *out = v;
         }
         g.sync();

@@ -215,9 +215,11 @@ struct StoreGrad {
 //   E   elements:    G_e = c (digamma(c + y) - digamma(c) - rowterm_n)
 //   B1  (r, k):      gk[r,k] = sum_n w_r(n) G_nk,  w_0 = 1, w_{1+d}(n) = x_nd
 //   B2  columns k:   chain rule to (alpha_k, b_offset_dk, ind_raw_dk), sigma_d by a group reduction
-template <typename T, int W, class Epi>
-__device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
-                                        uint32_t theta_off, const Group<W>& g, const Epi& epi) {
+// The pass comes in two halves (cf. dm_grad_items): `front` = effects, concentrations and row terms (F1-F3), `back` =
+// elements, column sums and the chain rule (E, B); the value pass only reads what the front half wrote.
+template <typename T, int W>
+__device__ __forceinline__ void dm_grad_front(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                              uint32_t theta_off, const Group<W>& g) {
     const int tid = g.tid;
     constexpr int TS = Group<W>::SIZE;
     const int K = dm.K, D = dm.D, K1 = dm.K1, DK1 = dm.DK1, N = dm.N, U = dt.U, ref = dt.ref;
@@ -227,16 +229,13 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
     const T* alpha = iraw + DK1;
     CPsi<T>* cp = sp<CPsi<T>>(cs.cp);
     T* rowterm = sp<T>(cs.rowterm);
-    T* G = sp<T>(cs.G);
     T* Ssm = sp<T>(cs.Gu);  // [U] row sums of the concentrations (small-U path)
     T* beta = sp<T>(cs.beta);
     T* ind = sp<T>(cs.ind);
-    T* gk = sp<T>(cs.gk);
     const T* xu = sp<T>(dt.xu);
     const T* ntot = sp<T>(dt.ntot);
     const int* grp = sp<int>(dt.grp);
     const int* rstart = sp<int>(dt.rstart);
-    const int* colperm = sp<int>(dt.colperm);
 
     // ---- F1: spike-and-slab effects of the thread's own columns (read back by the same thread in F2: no sync)
 #pragma unroll 1
@@ -310,6 +309,27 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
         }
     }
     g.sync();
+}
+
+template <typename T, int W, class Epi>
+__device__ __forceinline__ void dm_grad_back(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                             uint32_t theta_off, const Group<W>& g, const Epi& epi) {
+    const int tid = g.tid;
+    constexpr int TS = Group<W>::SIZE;
+    const int K = dm.K, D = dm.D, K1 = dm.K1, DK1 = dm.DK1, N = dm.N, U = dt.U, ref = dt.ref;
+    const T* sigma = sp<T>(theta_off);
+    const T* boff = sigma + D;
+    const T* iraw = boff + DK1;
+    const T* alpha = iraw + DK1;
+    const CPsi<T>* cp = sp<CPsi<T>>(cs.cp);
+    const T* rowterm = sp<T>(cs.rowterm);
+    T* G = sp<T>(cs.G);
+    const T* ind = sp<T>(cs.ind);
+    T* gk = sp<T>(cs.gk);
+    const T* xu = sp<T>(dt.xu);
+    const int* grp = sp<int>(dt.grp);
+    const int* rstart = sp<int>(dt.rstart);
+    const int* colperm = sp<int>(dt.colperm);
 
     // ---- E: elements  G = c (digamma(c+y) - digamma(c) - rowterm_n)
     if (dt.el_smem) {
@@ -509,6 +529,13 @@ __device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, c
         epi(D + 2 * DK1 + k, fma(alpha[k], T(-0.04), gk[k]));                            // d/d alpha_k
     }
     g.sync();
+}
+
+template <typename T, int W, class Epi>
+__device__ __forceinline__ void dm_grad(const Dims& dm, const DataTile<T>& dt, const ChainScratch& cs,
+                                        uint32_t theta_off, const Group<W>& g, const Epi& epi) {
+    dm_grad_front<T, W>(dm, dt, cs, theta_off, g);
+    dm_grad_back<T, W>(dm, dt, cs, theta_off, g, epi);
 }
 
 // Value of the log-density at theta.  Must follow dm_grad at the same theta (uses the c_uk it left in the
