@@ -278,18 +278,37 @@ __device__ __forceinline__ void dm_grad_front(const Dims& dm, const DataTile<T>&
             rowterm[n] = digamma_pos(S + ntot[n]) - digamma_pos(S);
         }
     } else {
+        if constexpr (W > 1) {
+            // several warps per chain: one (group, column) pair per thread and pass.  (The column-owner walk below
+            // leaves all but K threads idle for U dependent exp / digamma evaluations: with a continuous covariate,
+            // U = N, that was 43 % of the stall samples of a NUTS leaf.)
+            g.sync();
 #pragma unroll 1
-        for (int k = tid; k < K; k += TS) {
-            const T a = alpha[k];
-#pragma unroll 1
-            for (int u = 0; u < U; ++u) {
-                T eta = a;
+            for (int p = tid; p < U * K; p += TS) {
+                const int u = fast_div(p, dm.magicK);
+                const int k = p - u * K;
+                T eta = alpha[k];
 #pragma unroll 1
                 for (int d = 0; d < D; ++d) eta = fma(xu[u * D + d], beta[d * K + k], eta);
                 CPsi<T> v;
                 v.c = exp_acc(eta);
                 v.psi = digamma_pos(v.c);
-                cp[u * K + k] = v;
+                cp[p] = v;
+            }
+        } else {
+#pragma unroll 1
+            for (int k = tid; k < K; k += TS) {
+                const T a = alpha[k];
+#pragma unroll 1
+                for (int u = 0; u < U; ++u) {
+                    T eta = a;
+#pragma unroll 1
+                    for (int d = 0; d < D; ++d) eta = fma(xu[u * D + d], beta[d * K + k], eta);
+                    CPsi<T> v;
+                    v.c = exp_acc(eta);
+                    v.psi = digamma_pos(v.c);
+                    cp[u * K + k] = v;
+                }
             }
         }
         g.sync();
@@ -474,6 +493,22 @@ __device__ __forceinline__ void dm_grad_back(const Dims& dm, const DataTile<T>& 
             }
             gk[k] = g0;
         }
+    } else if (W > 1) {
+        // many groups, several warps per chain: one warp per (sum, column), the rows over its lanes
+        const int lane = tid & 31;
+#pragma unroll 1
+        for (int e = tid >> 5; e < (D + 1) * K; e += W) {
+            const int r = fast_div(e, dm.magicK);
+            const int kk = e - r * K;
+            const T* col = G + kk * N;
+            T s = T(0);
+#pragma unroll 1
+            for (int n = lane; n < N; n += 32) s = fma((r == 0) ? T(1) : xu[grp[n] * D + (r - 1)], col[n], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) gk[r * K + colperm[kk]] = s;
+        }
+        g.sync();
     } else {
 #pragma unroll 1
         for (int e = tid; e < (D + 1) * K; e += TS) {
