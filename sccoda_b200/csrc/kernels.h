@@ -84,7 +84,7 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
     const bool grouped = nimax > 0;
     size_t o = 0;
     p.ntot = o; o += rnd16((size_t)N * ts);
-    p.nrc = o; o += grouped ? rnd16((size_t)N * ts) : 0;          // per-row constants of the fp32 row terms (value pass)
+    p.nrc = o; o += rnd16((size_t)N * ts);                       // per-row constants of the fp32 row terms (value pass)
     p.xu = o; o += rnd16((size_t)Umax * D * ts);
     p.grp = o; o += rnd16((size_t)N * 4);
     p.rstart = o; o += rnd16((size_t)(Umax + 1) * 4);
@@ -96,7 +96,7 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
     p.ipair = o; o += grouped ? rnd16((size_t)nimax * 2) : 0;
     p.ipos = o; o += grouped ? rnd16((size_t)nimax * 2) : 0;
     p.inreal = o; o += grouped ? rnd16((size_t)nimax) : 0;
-    p.stage_red = o; o += grouped ? 32 * 8 : 0;                  // double[32]: one slot per warp for the staging sum
+    p.stage_red = o; o += 32 * 8;                                // double[32]: one slot per warp for the staging sum
     p.data_total = o;
     o = 0;
     p.red = o; o += rnd16((size_t)2 * W * 8);

@@ -70,7 +70,7 @@ __device__ __forceinline__ void stage_dataset(const KArgs& a, int b, const SmemP
     dt.oy = nullptr; dt.opair = nullptr; dt.opos = nullptr; dt.odesc = nullptr;
     dt.NI = 0; dt.NG = 0; dt.NImax = a.NImax; dt.NF = a.NF; dt.tot0 = Umax * K;
     dt.nrc = (uint32_t)pl.nrc;
-    if (a.grouped && sizeof(T) == 4) {
+    if (sizeof(T) == 4) {
         // value pass, row terms in fp32: per-row constants r(n) / lgamma(n) in fp64 here, sum_n lgamma(n) into the
         // constant (one partial per warp, added in warp order: independent of everything but the block size)
         T* nrc = sp<T>(dt.nrc);

@@ -659,7 +659,14 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
             }
     #pragma unroll 1
             for (; k < K; ++k) S0 += cu[k].c;
-            lp += lgamma_rowdiff_f64(((double)S0 + (double)S1) + ((double)S2 + (double)S3), (double)ntot[n]);
+            if constexpr (sizeof(T) == 4) {
+                // fp32 build: the cancellation-free joint form, as on the grouped layout (two fp64 logarithms per
+                // row otherwise, on the critical path of the value pass)
+                const T S = (S0 + S1) + (S2 + S3), nn = ntot[n], rc = sp<T>(dt.nrc)[n];
+                lp -= (double)(S >= T(6) ? lgamma_joint(S, nn, rc) : lgamma_shift(S, nn, rc) - lgamma_pos(S));
+            } else {
+                lp += lgamma_rowdiff_f64(((double)S0 + (double)S1) + ((double)S2 + (double)S3), (double)ntot[n]);
+            }
         }
     }
     // elements: lgamma(c + y) - lgamma(y); per-thread partial sums in T (<= a few dozen terms), total in fp64.
