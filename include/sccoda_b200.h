@@ -16,6 +16,9 @@
  *                                                                            sccoda/model/scCODA_model.py:821-827
  *   sccoda_sample_host    the same sampling call with HOST buffers (what a Python/ctypes caller that owns
  *                         numpy arrays binds; copies host<->device inside)
+ *   sccoda_pack           the input handling of CompositionalModel.__init__ (float64 cast, pseudocount, row sums)
+ *                                                                            sccoda/model/scCODA_model.py:90-100
+ *   sccoda_sample_raw_host  pack + sample from raw x / y host arrays (the end-to-end call the bench times)
  *
  * Conventions
  *   - plain pointers and sizes only; no framework types.  `stream` is a cudaStream_t passed as void*
@@ -205,6 +208,33 @@ int sccoda_sample_host(const sccoda_problem* prob_host, const sccoda_sampler* sm
                        void* stats, double* summary, int32_t summary_skip, int32_t device, float* kernel_ms);
 
 int sccoda_release_workspace(void);
+
+/* Host-side packer: raw inputs -> the packed layout above.  Replaces the input handling of
+ * CompositionalModel.__init__ (sccoda/model/scCODA_model.py:90-100: float64 cast, zeros -> 0.5 pseudocount BEFORE the
+ * row sums) for B datasets at once, threaded over datasets.
+ *   x [B,N,D], y [B,N,K] float64 (host), ref [B]; pseudocount != 0 applies the 0 -> 0.5 rule;
+ *   grouped: -1 = choose the gradient layout (pair/item for the designs the lane-per-cell-type kernels take and whenever
+ *   the item padding stays below 60 % of the counts, as long as the library's planner says it fits), 0 / 1 = force;
+ *   threads: 0 = all host cores.
+ * The handle owns every array; sccoda_packed_problem fills a sccoda_problem with HOST pointers into it (valid until
+ * sccoda_packed_free) — pass it to sccoda_sample_host, or copy the arrays to the device for sccoda_sample.
+ * Errors: -52 invalid reference index (the reference raises NameError, comp_ana.py:129-130), -55 the forced pair/item
+ * layout overflows its 16-bit indices. */
+typedef struct sccoda_packed sccoda_packed;
+int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, const double* y, const int32_t* ref,
+                int32_t dtype, int32_t pseudocount, int32_t grouped, int32_t threads, sccoda_packed** out);
+int sccoda_packed_problem(const sccoda_packed* pk, int32_t C, sccoda_problem* prob_host);
+const int32_t* sccoda_packed_row_order(const sccoda_packed* pk);  /* [B,N] original row of each packed row */
+const double* sccoda_packed_y(const sccoda_packed* pk);           /* [B,N,K] counts after the pseudocount, packed row order */
+const double* sccoda_packed_logp_const(const sccoda_packed* pk);  /* [B] multinomial-coefficient constant */
+void sccoda_packed_free(sccoda_packed* pk);
+
+/* The whole path from RAW host arrays: pack (above) + sccoda_sample_host.  x [B,N,D], y [B,N,K] float64, ref [B],
+ * init [B,C,P] (dtype).  timings_ms (may be NULL) receives [0] host time of the packer, [1] device time of the sampler
+ * launch, [2] wall time of the whole call. */
+int sccoda_sample_raw_host(int32_t B, int32_t N, int32_t K, int32_t D, int32_t C, const double* x, const double* y,
+                           const int32_t* ref, int32_t dtype, const sccoda_sampler* smp, const void* init, void* draws,
+                           void* stats, double* summary, int32_t summary_skip, int32_t device, float* timings_ms);
 
 /* Measurement utility for the bench: FP32 FFMA peak (TFLOP/s, 2 flop per FMA) and MUFU peak (T op/s) of the
  * current device, from two register-resident micro-kernels (best of 5). Synchronises `stream`. */

@@ -21,7 +21,9 @@ NCARRY = 8
 NSUM_PARAM, NSUM_BETA, NSUM_SCALAR = 2, 4, 6
 
 EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sample", "sccoda_summarize", "sccoda_predict",
-           "sccoda_launch_plan", "sccoda_kernel_kind", "sccoda_sample_host", "sccoda_release_workspace", "sccoda_measure_peaks")
+           "sccoda_launch_plan", "sccoda_kernel_kind", "sccoda_sample_host", "sccoda_release_workspace", "sccoda_measure_peaks",
+           "sccoda_pack", "sccoda_packed_problem", "sccoda_packed_row_order", "sccoda_packed_y", "sccoda_packed_logp_const",
+           "sccoda_packed_free", "sccoda_sample_raw_host")
 
 
 class Problem(ctypes.Structure):
@@ -87,6 +89,15 @@ def lib() -> ctypes.CDLL:
         _lib.sccoda_kernel_kind.argtypes = [pp, sp, ctypes.POINTER(i32)]
         _lib.sccoda_sample_host.argtypes = [pp, sp, vp, vp, vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float)]
         _lib.sccoda_measure_peaks.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), vp]
+        _lib.sccoda_pack.argtypes = [i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, ctypes.POINTER(vp)]
+        _lib.sccoda_packed_problem.argtypes = [vp, i32, pp]
+        for name in ("sccoda_packed_row_order", "sccoda_packed_y", "sccoda_packed_logp_const"):
+            getattr(_lib, name).argtypes = [vp]
+            getattr(_lib, name).restype = vp
+        _lib.sccoda_packed_free.argtypes = [vp]
+        _lib.sccoda_packed_free.restype = None
+        _lib.sccoda_sample_raw_host.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, i32, sp, vp, vp, vp, vp, i32, i32,
+                                                ctypes.POINTER(ctypes.c_float)]
     return _lib
 
 

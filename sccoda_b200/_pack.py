@@ -1,6 +1,10 @@
 """
 Host-side packer: raw (x, y, reference) -> the packed dataset layout of include/sccoda_b200.h.
 
+`pack` is a thin binding of the library's own packer (`sccoda_pack`, csrc/pack.cpp: C++, threaded over datasets —
+the one `sccoda_sample_raw_host` runs inside the end-to-end call).  `pack_numpy` is the same layout written in
+numpy; it documents the layout, and tests/test_pack_native.py holds the two to each other.
+
 Mirrors the input handling of CompositionalModel.__init__ (sccoda/model/scCODA_model.py:90-100): counts are
 cast to float64, zeros are replaced by a 0.5 pseudocount BEFORE the row sums are taken.  Rows are then sorted
 by covariate group (rows with identical covariate vectors share their concentrations, see csrc/model.cuh), the
@@ -192,7 +196,75 @@ def _no_items(B: int, K: int, Umax: int) -> dict:
                 opos=np.zeros((B, 1), np.uint16), odesc=np.zeros((B, 1), np.uint32), inreal=np.zeros((B, 2), np.uint8))
 
 
-def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) -> PackedProblem:
+def _normalise_inputs(x, y, ref):
+    """Shapes and errors shared by both packers (the reference's own checks: scCODA_model.py:110-113, comp_ana.py:129-130)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if y.ndim == 2:
+        y = y[None]
+    if x.ndim == 1:
+        x = x[:, None]
+    if x.ndim == 2:
+        x = np.broadcast_to(x[None], (y.shape[0],) + x.shape)
+    B, N, K = y.shape
+    if x.shape[0] != B or x.shape[1] != N:
+        raise ValueError("Wrong input dimensions X[{},:] != y[{},:]".format(x.shape[1], N))
+    ref = np.broadcast_to(np.asarray(ref, dtype=np.int32), (B,)).copy()
+    if np.any(ref < 0) or np.any(ref >= K):
+        raise NameError("Reference index is not a valid cell type name or numerical index!")
+    return np.ascontiguousarray(x), np.ascontiguousarray(y), ref
+
+
+def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None, threads: int = 0) -> PackedProblem:
+    """x: [B,N,D] or [N,D]; y: [B,N,K] or [N,K]; ref: int or [B].  Runs the library's packer (`sccoda_pack`) and copies
+    its arrays into a PackedProblem; arguments as in `pack_numpy`.  Raises when the native library is missing."""
+    import ctypes
+    from . import _native as nat
+    x, y, ref = _normalise_inputs(x, y, ref)
+    B, N, K = y.shape
+    D = x.shape[2]
+    dtype = np.dtype(dtype)
+    lib = nat.lib()
+    handle = ctypes.c_void_p()
+    rc = lib.sccoda_pack(B, N, K, D, x.ctypes.data, y.ctypes.data, ref.ctypes.data, nat.F32 if dtype.itemsize == 4 else nat.F64,
+                         int(bool(pseudocount)), -1 if grouped is None else int(bool(grouped)), int(threads),
+                         ctypes.byref(handle))
+    if rc in (-53, -55):
+        raise ValueError(lib.sccoda_last_error().decode("utf-8", "replace"))
+    nat.check(rc, "sccoda_pack")
+    try:
+        prob = nat.Problem()
+        nat.check(lib.sccoda_packed_problem(handle, 1, ctypes.byref(prob)), "sccoda_packed_problem")
+        Umax, NP = prob.Umax, prob.Umax * (K + 1)
+
+        def arr(addr, shape, dt):
+            n = int(np.prod(shape))
+            buf = (ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(addr)
+            return np.frombuffer(buf, dtype=dt, count=n).reshape(shape).copy()
+
+        ys = arr(lib.sccoda_packed_y(handle), (B, N, K), np.float64)
+        pk = PackedProblem(
+            B=B, N=N, K=K, D=D, Umax=Umax, dtype=dtype,
+            ey=arr(prob.ey, (B, N * K), dtype), eycst=arr(prob.eycst, (B, N * K), dtype),
+            eidx=arr(prob.eidx, (B, N * K), np.uint32), colperm=arr(prob.colperm, (B, K), np.int32),
+            nbig=arr(prob.nbig, (B,), np.int32), nbig_min=prob.nbig_min, y=ys.astype(dtype),
+            ntot=arr(prob.ntot, (B, N), dtype), xu=arr(prob.xu, (B, Umax, D), dtype), grp=arr(prob.grp, (B, N), np.int32),
+            rstart=arr(prob.rstart, (B, Umax + 1), np.int32), U=arr(prob.U, (B,), np.int32), ref=arr(prob.ref, (B,), np.int32),
+            lconst=arr(prob.lconst, (B,), np.float64),
+            row_order=arr(lib.sccoda_packed_row_order(handle), (B, N), np.int32).astype(np.int64),
+            logp_const=arr(lib.sccoda_packed_logp_const(handle), (B,), np.float64),
+            grouped=prob.grouped, NImax=prob.NImax, NOmax=prob.NOmax, NGmax=prob.NGmax, NF=prob.NF, NT=prob.NT, NOT=prob.NOT,
+            NI=arr(prob.NI, (B,), np.int32), NG=arr(prob.NG, (B,), np.int32), iy=arr(prob.iy, (B, ITEM_R, prob.NImax), dtype),
+            ipair=arr(prob.ipair, (B, prob.NImax), np.uint16), ipos=arr(prob.ipos, (B, prob.NImax), np.uint16),
+            inreal=arr(prob.inreal, (B, prob.NImax), np.uint8), pcoef=arr(prob.pcoef, (B, NP, 6), dtype),
+            oy=arr(prob.oy, (B, prob.NOmax), dtype), opair=arr(prob.opair, (B, prob.NGmax), np.uint16),
+            opos=arr(prob.opos, (B, prob.NGmax), np.uint16), odesc=arr(prob.odesc, (B, prob.NGmax), np.uint32))
+    finally:
+        lib.sccoda_packed_free(handle)
+    return pk
+
+
+def pack_numpy(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) -> PackedProblem:
     """x: [B,N,D] or [N,D]; y: [B,N,K] or [N,K]; ref: int or [B].
 
     grouped: None = choose (pair/item gradient path for the designs the lane-per-cell-type kernels take — at most 32
@@ -303,7 +375,7 @@ def pack(x, y, ref, dtype=np.float32, pseudocount: bool = True, grouped=None) ->
                          lconst=np.ascontiguousarray(lconst, np.float64),
                          row_order=np.stack(orders), logp_const=logp_const)
     if auto and pk.grouped and not _grouped_layout_fits(pk):
-        return pack(*args_in, dtype=dtype, pseudocount=pseudocount, grouped=False)
+        return pack_numpy(*args_in, dtype=dtype, pseudocount=pseudocount, grouped=False)
     return pk
 
 

@@ -9,8 +9,9 @@ mkdir -p "${obj}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Wno-deprecated-gpu-targets -Xcompiler -fPIC ${SCCODA_NVCC_EXTRA:-})
 pids=()
-for src in capi kernels kernels_f32 kernels_f64 kernels_f32g kernels_f64g kernels_cc kernels_mg summary predict peaks; do
-    "${NVCC}" "${FLAGS[@]}" -c -o "${obj}/${src}.o" "${here}/${src}.cu" > "${obj}/${src}.log" 2>&1 &
+for src in capi kernels kernels_f32 kernels_f64 kernels_f32g kernels_f64g kernels_cc kernels_mg summary predict peaks pack; do
+    ext=cu; [ -f "${here}/${src}.cpp" ] && ext=cpp
+    "${NVCC}" "${FLAGS[@]}" -c -o "${obj}/${src}.o" "${here}/${src}.${ext}" > "${obj}/${src}.log" 2>&1 &
     pids+=($!)
 done
 fail=0
@@ -19,5 +20,5 @@ cat "${obj}"/*.log
 if [ "${fail}" -ne 0 ]; then echo "nvcc failed" >&2; exit 1; fi
 "${NVCC}" -shared -Wno-deprecated-gpu-targets -o "${out}" "${obj}"/capi.o "${obj}"/kernels.o "${obj}"/kernels_f32.o "${obj}"/kernels_f64.o \
     "${obj}"/kernels_f32g.o "${obj}"/kernels_f64g.o "${obj}"/kernels_cc.o "${obj}"/kernels_mg.o \
-    "${obj}"/summary.o "${obj}"/predict.o "${obj}"/peaks.o
+    "${obj}"/summary.o "${obj}"/predict.o "${obj}"/peaks.o "${obj}"/pack.o -Xcompiler -pthread
 echo "built ${out}"

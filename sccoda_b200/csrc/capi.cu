@@ -3,7 +3,9 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/sccoda_b200.h"
@@ -26,6 +28,21 @@ int fail(int code, const char* fmt, ...) {
         cudaError_t e__ = (expr);                                                            \
         if (e__ != cudaSuccess) return fail(-100, "%s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
+
+}  // namespace
+
+namespace sccoda_capi {
+// error text for the translation units outside this file (pack.cpp)
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace sccoda_capi
+
+namespace {
 
 uint32_t magic_for(int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d); }
 
@@ -178,6 +195,7 @@ struct Workspace {
     int device = -1;
 };
 Workspace g_ws;
+std::mutex g_ws_mutex;   // sccoda_sample_host calls share the cached workspace: one at a time
 
 int workspace_get(int device, size_t bytes, void** out) {
     if (g_ws.ptr != nullptr && (g_ws.device != device || g_ws.bytes < bytes)) {
@@ -206,6 +224,7 @@ extern "C" {
 int sccoda_version(void) { return 100; }
 
 int sccoda_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
     if (g_ws.ptr != nullptr) cudaFree(g_ws.ptr);
     g_ws = Workspace{};
     return 0;
@@ -314,6 +333,7 @@ int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, cons
     if (!ph || !smp || !init) return fail(-40, "NULL argument");
     if (ph->B < 1 || ph->C < 1 || ph->N < 1 || ph->K < 2 || ph->D < 1 || ph->Umax < 1) return fail(-41, "bad problem dimensions");
     if (smp->num_results < 1) return fail(-12, "need num_results >= 1");
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
     CUDA_TRY(cudaSetDevice(device));
     const size_t ts = ph->dtype == SCCODA_F64 ? 8 : 4;
     const size_t B = ph->B, C = ph->C, N = ph->N, K = ph->K, D = ph->D, U = ph->Umax, S = smp->num_results;
@@ -393,9 +413,33 @@ int sccoda_sample_host(const sccoda_problem* ph, const sccoda_sampler* smp, cons
         if (e != cudaSuccess) { rc = fail(-44, "kernel/copy failed: %s", cudaGetErrorString(e)); break; }
         if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
     } while (0);
+    if (rc) cudaStreamSynchronize(st);   // error path: nothing may still be copying into the cached workspace
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     cudaStreamDestroy(st);
+    return rc;
+}
+
+int sccoda_sample_raw_host(int32_t B, int32_t N, int32_t K, int32_t D, int32_t C, const double* x, const double* y,
+                           const int32_t* ref, int32_t dtype, const sccoda_sampler* smp, const void* init, void* draws,
+                           void* stats, double* summary, int32_t summary_skip, int32_t device, float* timings_ms) {
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    sccoda_packed* pk = nullptr;
+    int rc = sccoda_pack(B, N, K, D, x, y, ref, dtype, 1, -1, 0, &pk);
+    if (rc) return rc;
+    const auto t1 = clk::now();
+    sccoda_problem prob;
+    sccoda_packed_problem(pk, C, &prob);
+    float kernel_ms = 0.0f;
+    rc = sccoda_sample_host(&prob, smp, init, draws, stats, summary, summary_skip, device, &kernel_ms);
+    sccoda_packed_free(pk);
+    const auto t2 = clk::now();
+    if (timings_ms) {
+        timings_ms[0] = std::chrono::duration<float, std::milli>(t1 - t0).count();
+        timings_ms[1] = kernel_ms;
+        timings_ms[2] = std::chrono::duration<float, std::milli>(t2 - t0).count();
+    }
     return rc;
 }
 

@@ -442,7 +442,12 @@ static __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off,
 // ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ KArgs a) {
+// The body is shared by two entry points that differ in their register budget only:
+//   hmc_cc_kernel      72 registers, 7 CTAs of 128 threads per SM: every chain of a full sweep (>= ~2400 chains) resident
+//   hmc_cc_lat_kernel  no register cap: for launches that leave the device under-filled (a shard of the sweep on each
+//                      of 8 GPUs: 512 chains on 592 schedulers), where one warp per scheduler runs at the latency of its
+//                      own dependency chains and the spills / re-materialisations of the capped build are pure loss
+__device__ __forceinline__ void hmc_cc_body(const KArgs& a) {
     using T = float;
     const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
     const int cpc = blockDim.x >> 5;
@@ -584,6 +589,9 @@ __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ 
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
 }
+
+__global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ KArgs a) { hmc_cc_body(a); }
+__global__ void __launch_bounds__(128, 1) hmc_cc_lat_kernel(const __grid_constant__ KArgs a) { hmc_cc_body(a); }
 
 // ------------------------------------------------------------------------------------------------
 // K3cc — NUTS for the same case/control shape: the iterative tree of nuts_kernel (kernels_impl.cuh; [TFP]
