@@ -162,6 +162,13 @@ typedef struct sccoda_sampler {
     int32_t freeze_spike_slab; /* 1 = sigma_d and ind_raw keep their initial values (zero momentum, zero gradient): with
                                   sigma_d = 1 and ind_raw = 1 the density is SimpleModel's (sccoda/model/other_models.py:31-109,
                                   beta = b_offset) up to a constant */
+    double reject_conc_above;  /* Concentration guard.  A state with some c_uk = exp(alpha_k + x_u . beta_k) above this limit
+                                  gets a NaN log-density and is therefore rejected.  0 = default of the arithmetic type
+                                  (1e6 in fp32: the validated range of the fp32 lgamma forms; 1e15 in fp64: where the
+                                  reference's own fp64 differences lgamma(c+y) - lgamma(c), scCODA_model.py:746-751, lose
+                                  every digit and evaluate to the bare multinomial constant — a spurious mode);
+                                  negative or +inf = no guard (with SCCODA_F64 this is the reference's arithmetic, trap
+                                  included); any other positive value = that limit.  DESIGN.md §Numerics. */
 } sccoda_sampler;
 
 /* Library / device info. */
@@ -170,6 +177,14 @@ const char* sccoda_last_error(void);
 
 /* Value and gradient of the log-density at theta[B,C,P] -> logp[B,C] (f64), grad[B,C,P] (dtype). */
 int sccoda_logp_grad(const sccoda_problem* prob, const void* theta, double* logp, void* grad, void* stream);
+
+/* The same evaluation through the device functions of a given sampler kernel family: kernel_kind as reported by
+ * sccoda_kernel_kind (0, 1, 2 = the generic kernels; 3, 4 = the case/control kernels' cc_grad / cc_value; 5, 6 = the
+ * multi-group kernels' mg_grad / mg_value) — so that value and gradient of the kernels a sweep actually runs can be
+ * compared with the reference density at identical states.  Fails (-25) when the problem does not have the shape that
+ * family takes.  reject_conc_above: as in sccoda_sampler. */
+int sccoda_logp_grad_as(const sccoda_problem* prob, int32_t kernel_kind, double reject_conc_above, const void* theta,
+                        double* logp, void* grad, void* stream);
 
 /* Run the sampler.  init[B,C,P]; draws[B,C,S,P]; stats[B,C,S,SCCODA_NSTAT]; carry[B,C,P+SCCODA_NCARRY] f64
  * (may be NULL when step_begin==0 and the run is not chunked). All device pointers. */

@@ -35,6 +35,8 @@ def lib():
                                        + [ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint32,
                                           dp, dp, ctypes.c_int])
         _LIB.oracle_max_threads.restype = ctypes.c_int
+        _LIB.oracle_set_reject_conc_above.argtypes = [ctypes.c_double]
+        _LIB.oracle_set_reject_conc_above.restype = None
     return _LIB
 
 
@@ -55,8 +57,12 @@ def logp_grad(x, y, n_total, logp_const, ref, theta):
 
 def sample(x, y, n_total, logp_const, ref, init, method, num_results, num_burnin, num_adapt=None,
            num_leapfrog=10, max_tree_depth=10, step_size=0.01, target_accept=0.75, seed=0, chain_id0=0,
-           n_threads=0):
-    """x[B,N,D] y[B,N,K] n_total[B,N] logp_const[B] ref[B] init[B,C,P] -> draws[B,C,S,P], stats dict of [B,C,S]."""
+           n_threads=0, reject_conc_above=None):
+    """x[B,N,D] y[B,N,K] n_total[B,N] logp_const[B] ref[B] init[B,C,P] -> draws[B,C,S,P], stats dict of [B,C,S].
+
+    reject_conc_above: None = the reference's arithmetic (no guard); a limit = states with a concentration above it
+    are rejected, as the device kernels do (sccoda_sampler::reject_conc_above)."""
+    lib().oracle_set_reject_conc_above(float(reject_conc_above) if reject_conc_above else 0.0)
     x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
     n_total = np.ascontiguousarray(n_total, np.float64)
     logp_const = np.ascontiguousarray(logp_const, np.float64)
@@ -74,6 +80,7 @@ def sample(x, y, n_total, logp_const, ref, init, method, num_results, num_burnin
                         _dp(logp_const), _dp(init), int(method), int(num_results), int(num_burnin), int(num_adapt),
                         int(num_leapfrog), int(max_tree_depth), float(step_size), float(target_accept),
                         int(seed), int(chain_id0), _dp(draws), _dp(stats), int(n_threads))
+    lib().oracle_set_reject_conc_above(0.0)
     return draws, {k: stats[..., i] for i, k in enumerate(STAT_NAMES)}
 
 

@@ -92,6 +92,12 @@ typedef struct {
     double logp_const;
 } model_t;
 
+/* Optional concentration guard (NOT part of the reference: its density is evaluated for any concentration).  When set,
+ * a state with some concentration above the limit gets a NaN value => rejected by the samplers, which is what the
+ * device kernels do by default (sccoda_sampler::reject_conc_above).  Default: off = the reference's arithmetic. */
+static double g_conc_max = INFINITY;
+void oracle_set_reject_conc_above(double limit) { g_conc_max = (limit > 0.0) ? limit : INFINITY; }
+
 typedef struct { double *beta, *ind, *conc, *G, *g; } work_t; /* [D*K], [D*(K-1)], [N*K], [N*K], [D*K] */
 
 static void work_alloc(work_t *w, const model_t *m) {
@@ -143,6 +149,7 @@ static double logp_grad(const model_t *m, work_t *w, const double *theta, double
             double c = exp(eta);                                               /* :743 */
             w->conc[n * K + k] = c;
             S += c;
+            if (want_value && c > g_conc_max) lp = NAN;
         }
         if (want_value) {                                                      /* DirichletMultinomial :746-751 [TFP] */
             for (int k = 0; k < K; ++k)

@@ -130,6 +130,9 @@ class ModelData:
     ref: int               # reference cell type index
     logp_const: float      # sum_n [lgamma(n_n+1) - sum_k lgamma(y_nk+1)]
     freeze: bool = False   # SimpleModel runs: sigma_d and ind_raw keep their values (zero momentum, zero gradient)
+    # NOT part of the reference (its density is evaluated for any concentration): when finite, a state with a
+    # concentration above the limit has a NaN value => rejected, as the device kernels do by default
+    reject_conc_above: float = float("inf")
 
     def frozen_mask(self) -> np.ndarray:
         """True for the parameters a SimpleModel run holds fixed (sigma_d and ind_raw)."""
@@ -212,6 +215,8 @@ def logp(theta: np.ndarray, m: ModelData) -> float:
         lp_alpha = np.sum(-0.5 * (alpha / 5.0) ** 2 - math.log(5.0) - 0.5 * LOG_2PI)  # :736-741
         _, _, beta = _beta_full(sigma, boff, iraw, m)
         conc = np.exp(alpha[None, :] + m.x @ beta)            # :743
+        if np.any(conc > m.reject_conc_above):
+            return float("nan")
         S = conc.sum(axis=1)
         # DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c) + log_combinations(n, y)   (:746-751)
         lp_dm = (np.sum(gammaln(conc + m.y) - gammaln(conc))

@@ -20,7 +20,7 @@ STAT_NAMES = ("target_log_prob", "log_accept_ratio", "is_accepted", "step_size",
 NCARRY = 8
 NSUM_PARAM, NSUM_BETA, NSUM_SCALAR = 2, 4, 6
 
-EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_sample", "sccoda_summarize", "sccoda_predict",
+EXPORTS = ("sccoda_version", "sccoda_last_error", "sccoda_logp_grad", "sccoda_logp_grad_as", "sccoda_sample", "sccoda_summarize", "sccoda_predict",
            "sccoda_launch_plan", "sccoda_kernel_kind", "sccoda_sample_host", "sccoda_release_workspace", "sccoda_measure_peaks",
            "sccoda_pack", "sccoda_packed_problem", "sccoda_packed_row_order", "sccoda_packed_y", "sccoda_packed_logp_const",
            "sccoda_packed_free", "sccoda_sample_raw_host")
@@ -61,7 +61,8 @@ class Sampler(ctypes.Structure):
                 ("step_size", ctypes.c_double), ("target_accept", ctypes.c_double),
                 ("seed", ctypes.c_uint64), ("chain_id0", ctypes.c_uint32), ("warps_per_chain", ctypes.c_int32),
                 ("store_draws", ctypes.c_int32), ("chains_per_cta", ctypes.c_int32),
-                ("generic_only", ctypes.c_int32), ("freeze_spike_slab", ctypes.c_int32)]
+                ("generic_only", ctypes.c_int32), ("freeze_spike_slab", ctypes.c_int32),
+                ("reject_conc_above", ctypes.c_double)]
 
 
 _lib = None
@@ -82,6 +83,7 @@ def lib() -> ctypes.CDLL:
         _lib.sccoda_version.restype = ctypes.c_int
         _lib.sccoda_last_error.restype = ctypes.c_char_p
         _lib.sccoda_logp_grad.argtypes = [pp, vp, vp, vp, vp]
+        _lib.sccoda_logp_grad_as.argtypes = [pp, i32, ctypes.c_double, vp, vp, vp, vp]
         _lib.sccoda_sample.argtypes = [pp, sp, vp, vp, vp, vp, vp]
         _lib.sccoda_summarize.argtypes = [pp, i32, i32, vp, vp, vp, vp]
         _lib.sccoda_predict.argtypes = [pp, vp, i32, i32, i32, vp, vp, vp, vp]

@@ -392,7 +392,8 @@ def _grouped_layout_fits(pk: PackedProblem) -> bool:
     prob = nat.Problem(C=1, **nat.problem_fields(pk, lambda name: getattr(pk, name).ctypes.data))
     smp = nat.Sampler(method=nat.METHOD_NUTS, num_results=1, num_burnin=0, num_adapt=0, num_leapfrog=10, max_tree_depth=10,
                       step_begin=0, step_end=0, step_size=0.01, target_accept=0.75, seed=0, chain_id0=0,
-                      warps_per_chain=0, store_draws=1, chains_per_cta=0, generic_only=0, freeze_spike_slab=0)
+                      warps_per_chain=0, store_draws=1, chains_per_cta=0, generic_only=0, freeze_spike_slab=0,
+                      reject_conc_above=0.0)
     out = [ctypes.c_int32() for _ in range(4)]
     rc = lib.sccoda_launch_plan(ctypes.byref(prob), ctypes.byref(smp), *(ctypes.byref(v) for v in out))
     return rc != -9

@@ -1,6 +1,7 @@
 // C ABI (extern "C") of libsccoda_b200.so — see include/sccoda_b200.h.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <chrono>
@@ -83,12 +84,21 @@ int validate(const sccoda_problem* p) {
     return 0;
 }
 
+// sccoda_sampler::reject_conc_above: 0 = the default of the arithmetic type, negative or infinite = no limit
+double default_conc_max(int dtype) { return dtype == SCCODA_F32 ? 1e6 : 1e15; }
+double conc_max_from(double reject_conc_above, int dtype) {
+    if (reject_conc_above == 0.0) return default_conc_max(dtype);
+    if (reject_conc_above < 0.0) return (double)INFINITY;
+    return reject_conc_above;
+}
+
 void fill_dims(const sccoda_problem* p, sccoda::KArgs& a) {
     a.dm.N = p->N; a.dm.K = p->K; a.dm.D = p->D;
     a.dm.K1 = p->K - 1; a.dm.DK1 = p->D * (p->K - 1); a.dm.NK = p->N * p->K;
     a.dm.P = p->D + 2 * a.dm.DK1 + p->K;
     a.dm.magicK = magic_for(p->K);
     a.dm.magicK1 = magic_for(p->K - 1);  // 0 encodes a divisor of 1 (K == 2)
+    a.dm.conc_max = default_conc_max(p->dtype);
     a.B = p->B; a.C = p->C; a.Umax = p->Umax;
     a.ey = p->ey; a.eycst = p->eycst; a.eidx = p->eidx; a.colperm = p->colperm; a.nbig = p->nbig;
     a.ntot = p->ntot; a.xu = p->xu;
@@ -165,7 +175,7 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, i
     return fail(-9, "problem does not fit the shared memory of one CTA");
 }
 
-int fill_sampler(const sccoda_sampler* s, sccoda::KArgs& a, int* kind) {
+int fill_sampler(const sccoda_sampler* s, sccoda::KArgs& a, int* kind, int dtype) {
     if (!s) return fail(-10, "sampler is NULL");
     if (s->method < 0 || s->method > 2) return fail(-11, "unknown method %d", s->method);
     if (s->num_results < 1 || s->num_burnin < 0) return fail(-12, "need num_results >= 1 and num_burnin >= 0");
@@ -182,6 +192,8 @@ int fill_sampler(const sccoda_sampler* s, sccoda::KArgs& a, int* kind) {
     a.store_draws = s->store_draws;
     a.generic_only = s->generic_only ? 1 : 0;
     a.dm.freeze = s->freeze_spike_slab ? 1 : 0;
+    if (s->reject_conc_above != s->reject_conc_above) return fail(-17, "reject_conc_above is NaN");
+    a.dm.conc_max = conc_max_from(s->reject_conc_above, dtype);
     a.step_size = s->step_size; a.target_accept = s->target_accept; a.seed = s->seed; a.chain_id0 = s->chain_id0;
     *kind = s->method == SCCODA_METHOD_NUTS ? sccoda::KIND_NUTS : sccoda::KIND_HMC;
     return 0;
@@ -239,7 +251,7 @@ int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, in
     sccoda::KArgs a{};
     fill_dims(prob, a);
     int kind = 0;
-    rc = fill_sampler(smp, a, &kind);
+    rc = fill_sampler(smp, a, &kind, prob->dtype);
     if (rc) return rc;
     Plan pl;
     rc = make_plan(prob, a, kind, smp->warps_per_chain, smp->chains_per_cta, &pl);
@@ -257,7 +269,7 @@ int sccoda_kernel_kind(const sccoda_problem* prob, const sccoda_sampler* smp, in
     sccoda::KArgs a{};
     fill_dims(prob, a);
     int kind = 0;
-    rc = fill_sampler(smp, a, &kind);
+    rc = fill_sampler(smp, a, &kind, prob->dtype);
     if (rc) return rc;
     Plan pl;
     rc = make_plan(prob, a, kind, smp->warps_per_chain, smp->chains_per_cta, &pl);
@@ -281,6 +293,44 @@ int sccoda_logp_grad(const sccoda_problem* prob, const void* theta, double* logp
     return 0;
 }
 
+int sccoda_logp_grad_as(const sccoda_problem* prob, int32_t kernel_kind, double reject_conc_above, const void* theta,
+                        double* logp, void* grad, void* stream) {
+    int rc = validate(prob);
+    if (rc) return rc;
+    if (!theta || !logp || !grad) return fail(-20, "theta/logp/grad must not be NULL");
+    if (reject_conc_above != reject_conc_above) return fail(-17, "reject_conc_above is NaN");
+    sccoda::KArgs a{};
+    fill_dims(prob, a);
+    a.dm.conc_max = conc_max_from(reject_conc_above, prob->dtype);
+    a.init = theta; a.draws = grad; a.carry = logp;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (kernel_kind == sccoda::KIND_HMC || kernel_kind == sccoda::KIND_NUTS || kernel_kind == 0) {
+        a.generic_only = 1;
+        Plan pl;
+        int kind = sccoda::KIND_LOGP;
+        rc = make_plan(prob, a, kind, 0, 0, &pl);
+        if (rc) return rc;
+        CUDA_TRY(sccoda::launch_kernel(kind, prob->dtype, pl.W, pl.cpc, a, st));
+        return 0;
+    }
+    const bool cc = kernel_kind == sccoda::KIND_HMC_CC || kernel_kind == sccoda::KIND_NUTS_CC;
+    const bool mg = kernel_kind == sccoda::KIND_HMC_MG || kernel_kind == sccoda::KIND_NUTS_MG;
+    if (!cc && !mg) return fail(-24, "unknown kernel kind %d", kernel_kind);
+    if (cc ? !sccoda::fits_cc(a, prob->dtype) : !sccoda::fits_mg(a, prob->dtype))
+        return fail(-25, "the problem does not have the shape kernel kind %d takes (fp32, pair/item layout, %s)", kernel_kind,
+                    cc ? "D == 1, two covariate groups, K <= 31" : "<= 32 covariate groups, D <= 4 with K <= 31 or D <= 3 with K <= 62");
+    int dev = 0, max_smem = 227 * 1024;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int kk = cc ? sccoda::KIND_HMC_CC : sccoda::KIND_HMC_MG;
+    int cpc = prob->C < 4 ? prob->C : 4;
+    while (cpc > 1 && (int)sccoda::smem_bytes_for(a, kk, 1, cpc, prob->dtype) > max_smem) cpc -= 1;
+    const size_t smem = sccoda::smem_bytes_for(a, kk, 1, cpc, prob->dtype);
+    if ((int)smem > max_smem) return fail(-9, "problem needs %zu bytes of shared memory per chain group, device limit is %d", smem, max_smem);
+    const int grid = prob->B * ((prob->C + cpc - 1) / cpc);
+    CUDA_TRY(cc ? sccoda::launch_logp_cc(a, grid, cpc * 32, smem, st) : sccoda::launch_logp_mg(a, grid, cpc * 32, smem, st));
+    return 0;
+}
+
 int sccoda_sample(const sccoda_problem* prob, const sccoda_sampler* smp, const void* init, void* draws, void* stats,
                   double* carry, void* stream) {
     int rc = validate(prob);
@@ -288,7 +338,7 @@ int sccoda_sample(const sccoda_problem* prob, const sccoda_sampler* smp, const v
     sccoda::KArgs a{};
     fill_dims(prob, a);
     int kind = 0;
-    rc = fill_sampler(smp, a, &kind);
+    rc = fill_sampler(smp, a, &kind, prob->dtype);
     if (rc) return rc;
     if (a.step_begin == 0 && !init) return fail(-21, "init must not be NULL when step_begin == 0");
     if (a.step_begin > 0 && !carry) return fail(-22, "carry must not be NULL when resuming (step_begin > 0)");

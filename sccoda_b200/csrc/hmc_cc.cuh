@@ -140,6 +140,7 @@ struct CcTile {
     int NT, NOT;                     // items / odd counts of the fullest pair of THIS dataset (loop bounds)
     int N, NK, nbig;
     float cnt0, cnt1;                // rows of the two covariate groups
+    float c_max;                     // rejection limit of the concentrations (Dims::conc_max)
     double lconst;
 };
 
@@ -159,6 +160,7 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
     const int N = a.dm.N, K = a.dm.K, NK = a.dm.NK, NP = 2 * (K + 1);
     t.cf = (uint32_t)pl.cf; t.yv = (uint32_t)pl.yv; t.ov = (uint32_t)pl.ov; t.rows = (uint32_t)pl.rows; t.el = (uint32_t)pl.el;
     t.N = N; t.NK = NK;
+    t.c_max = (float)a.dm.conc_max;
     // [0]: items, [1]: odd counts of the fullest pair of this dataset, [2]: elements with a count >= 6
     int* bounds = sp<int>((uint32_t)pl.bounds);
     if (threadIdx.x < 2) bounds[threadIdx.x] = 0;
@@ -372,7 +374,7 @@ static __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off,
     if (lane == 0 && qs >= 0.0f) lp -= (double)log1pf(qs * qs);
     // DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c)                               (:746-751)
     // Guard (numerics): beyond c_max the lgamma differences have lost all precision => NaN => rejected.
-    const float c_max = 1e6f, c_joint = SCCODA_C_JOINT;
+    const float c_max = t.c_max, c_joint = SCCODA_C_JOINT;
     bool need_fix = false, bad = false;
     if (has) {
         float acc = 0.0f;
@@ -591,6 +593,57 @@ __device__ __forceinline__ void hmc_cc_body(const KArgs& a) {
 }
 
 __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ KArgs a) { hmc_cc_body(a); }
+
+// K1cc — value and gradient at given states through cc_grad / cc_value, i.e. exactly what the sampler above evaluates
+// at every leapfrog (sccoda_logp_grad_as; target_log_prob_fn + autodiff of scCODA_model.py:756-760): theta[B,C,P] in
+// a.init, gradient to a.draws, value to a.carry[chain].
+__global__ void __launch_bounds__(128) logp_grad_cc_kernel(const __grid_constant__ KArgs a) {
+    using T = float;
+    const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
+    const int cpc = blockDim.x >> 5;
+    const int ctas_per_ds = (a.C + cpc - 1) / cpc;
+    const int b = blockIdx.x / ctas_per_ds;
+    const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
+    const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P;
+    const CcPlan pl = plan_cc(a.dm.N, K, a.NT, a.NOT, 0);
+    CcTile tile;
+    cc_stage(a, b, pl, tile);
+    if (c >= a.C) return;
+    const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
+    const uint32_t pc_off = chain_off + (uint32_t)pl.pc;
+    T* const vec = sp<T>(chain_off + (uint32_t)pl.vec);
+    const size_t chain = (size_t)b * a.C + c;
+    const int ref = a.ref[b];
+    CcLane ln;
+    ln.K = K;
+    ln.has = lane < K;
+    ln.active = ln.has && lane != ref;
+    {
+        const T* xu = static_cast<const T*>(a.xu) + (size_t)b * 2;
+        ln.x0 = xu[0];
+        ln.x1 = a.U[b] > 1 ? xu[1] : T(0);
+    }
+    const int jj = lane - (lane > ref);
+    const int ix_b = 1 + jj, ix_i = 1 + K1 + jj, ix_a = 1 + 2 * K1 + lane;
+    const T* theta = static_cast<const T*>(a.init) + chain * P;
+    for (int i = lane; i < P; i += 32) vec[i] = theta[i];
+    __syncwarp();
+    CcVec q;
+    q.s = vec[0];
+    q.a = ln.has ? vec[ix_a] : T(0);
+    q.b = ln.active ? vec[ix_b] : T(0);
+    q.i = ln.active ? vec[ix_i] : T(0);
+    const CcGrad gr = cc_grad(tile, ln, q, lane);
+    const double lp = cc_value(tile, pc_off, ln.has, q.a, q.b, q.i, q.s, gr.c, K, lane);
+    T* out = static_cast<T*>(a.draws) + chain * P;
+    if (lane == 0) out[0] = gr.g.s;
+    if (ln.has) out[ix_a] = gr.g.a;
+    if (ln.active) {
+        out[ix_b] = gr.g.b;
+        out[ix_i] = gr.g.i;
+    }
+    if (lane == 0) a.carry[chain] = lp;
+}
 __global__ void __launch_bounds__(128, 1) hmc_cc_lat_kernel(const __grid_constant__ KArgs a) { hmc_cc_body(a); }
 
 // ------------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ struct MgTile {
     uint32_t yv_stride, ov_stride;                 // bytes per (pair of groups, column slot)
     int UP, UPmax;                                 // pairs of groups of THIS dataset / of the fullest dataset of the batch
     int N, NK, nbig;
+    float c_max;                                   // rejection limit of the concentrations (Dims::conc_max)
     double lconst;
 };
 
@@ -53,6 +54,7 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
     t.cnt = pin_u32((uint32_t)pl.cnt); t.bnd = pin_u32((uint32_t)pl.bounds);
     t.yv_stride = pin_u32((uint32_t)(NT * kItemR * 32 * 8)); t.ov_stride = pin_u32((uint32_t)(NOT * 32 * 8));
     t.N = N; t.NK = NK;
+    t.c_max = (float)a.dm.conc_max;
     t.UP = (a.U[b] + 1) >> 1;
     t.UPmax = UPmax;
     const int CS = 32 * NS, NQ = UPmax * NS;
@@ -356,7 +358,7 @@ static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off,
     double lp = (double)prior;
     // DirichletMultinomial [TFP]: lbeta(c+y) - lbeta(c)                               (:746-751)
     // Guard (numerics): beyond c_max the lgamma differences have lost all precision => NaN => rejected.
-    const float c_max = 1e6f, c_joint = SCCODA_C_JOINT;
+    const float c_max = t.c_max, c_joint = SCCODA_C_JOINT;
     bool need_fix = false, bad = false;
     {
         const float* cnt = sp<float>(t.cnt);
@@ -625,6 +627,41 @@ __global__ void __launch_bounds__(128, mg_hmc_ctas(D, NS)) hmc_mg_kernel(const _
     mp.scatter(vec, thc, lane);
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
+}
+
+// K1mg — value and gradient at given states through mg_grad / mg_value (sccoda_logp_grad_as): theta[B,C,P] in a.init,
+// gradient to a.draws, value to a.carry[chain].
+template <int D, int NS>
+__global__ void __launch_bounds__(128) logp_grad_mg_kernel(const __grid_constant__ KArgs a) {
+    using T = float;
+    using V = MgVec<D, NS>;
+    const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
+    const int cpc = blockDim.x >> 5;
+    const int ctas_per_ds = (a.C + cpc - 1) / cpc;
+    const int b = blockIdx.x / ctas_per_ds;
+    const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
+    const int K = a.dm.K, P = a.dm.P;
+    const int UPmax = (a.Umax + 1) >> 1;
+    const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, NS, a.NT, a.NOT, 0);
+    MgTile tile;
+    mg_stage(a, b, pl, UPmax, NS, tile);
+    if (c >= a.C) return;
+    const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
+    const uint32_t pc_off = pin_u32(chain_off + (uint32_t)pl.pc);
+    T* const vec = sp<T>(pin_u32(chain_off + (uint32_t)pl.vec));
+    const size_t chain = (size_t)b * a.C + c;
+    MgMap<D, NS> mp;
+    mp.init(K, a.ref[b], lane);
+    const T* theta = static_cast<const T*>(a.init) + chain * P;
+    for (int i = lane; i < P; i += 32) vec[i] = theta[i];
+    __syncwarp();
+    const V q = mp.gather(vec);
+    const V gr = mg_grad<D, NS>(tile, mp.ln, q, pc_off, lane);
+    bool neg_sigma;
+    const float prior = mg_prior<D, NS>(q, lane, neg_sigma);
+    const double lp = mg_value<NS>(tile, pc_off, mp.ln.hasmask(), prior, neg_sigma, lane);
+    mp.scatter(static_cast<T*>(a.draws) + chain * P, gr, lane);
+    if (lane == 0) a.carry[chain] = lp;
 }
 
 // ------------------------------------------------------------------------------------------------

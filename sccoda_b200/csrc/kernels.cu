@@ -12,12 +12,18 @@ int nvec_for(int kind, int max_depth) {
     return 15 + 2 * (max_depth + 1);
 }
 
+bool fits_cc(const KArgs& a, int dtype) {
+    return a.grouped && dtype == SCCODA_F32 && a.dm.D == 1 && a.Umax == 2 && a.dm.K <= 31;
+}
+bool fits_mg(const KArgs& a, int dtype) {
+    return a.grouped && dtype == SCCODA_F32 && a.Umax <= kMgMaxGroups &&
+           (a.dm.K <= 31 ? a.dm.D <= kMgMaxD : (a.dm.K <= kMgMaxK && a.dm.D <= kMgMaxD2));
+}
+
 int select_kind(const KArgs& a, int kind, int dtype, int W) {
-    if ((kind == KIND_HMC || kind == KIND_NUTS) && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 &&
-        a.dm.D == 1 && a.Umax == 2 && a.dm.K <= 31)
+    if ((kind == KIND_HMC || kind == KIND_NUTS) && !a.generic_only && W == 1 && fits_cc(a, dtype))
         return kind == KIND_HMC ? KIND_HMC_CC : KIND_NUTS_CC;
-    if ((kind == KIND_HMC || kind == KIND_NUTS) && !a.generic_only && a.grouped && dtype == SCCODA_F32 && W == 1 &&
-        a.Umax <= kMgMaxGroups && (a.dm.K <= 31 ? a.dm.D <= kMgMaxD : (a.dm.K <= kMgMaxK && a.dm.D <= kMgMaxD2)))
+    if ((kind == KIND_HMC || kind == KIND_NUTS) && !a.generic_only && W == 1 && fits_mg(a, dtype))
         return kind == KIND_HMC ? KIND_HMC_MG : KIND_NUTS_MG;
     return kind;
 }

@@ -175,6 +175,11 @@ int select_kind(const KArgs& a, int kind, int dtype, int W);
 cudaError_t launch_hmc_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t launch_nuts_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t launch_hmc_mg(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_logp_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_logp_mg(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
+// does the problem have the shape the case/control (cc) / multi-group (mg) lane-per-cell-type kernels are written for?
+bool fits_cc(const KArgs& a, int dtype);
+bool fits_mg(const KArgs& a, int dtype);
 cudaError_t launch_nuts_mg(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st);
 size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int dtype);
 cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const KArgs& a, cudaStream_t st);

@@ -11,6 +11,12 @@ cudaError_t launch_hmc_cc(const KArgs& a, int grid, int block, size_t smem, cuda
     fn<<<grid, block, smem, st>>>(a);
     return cudaGetLastError();
 }
+cudaError_t launch_logp_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(logp_grad_cc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    logp_grad_cc_kernel<<<grid, block, smem, st>>>(a);
+    return cudaGetLastError();
+}
 cudaError_t launch_nuts_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(nuts_cc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -43,6 +43,7 @@ struct Dims {
     int NK;    // N*K
     uint32_t magicK, magicK1;  // ceil(2^32/K), ceil(2^32/(K-1)); 0 encodes a divisor of 1
     int freeze;                // 1: sigma_d and ind_raw are frozen (zero momentum, zero gradient): SimpleModel
+    double conc_max;           // states with a concentration above this get a NaN value => rejected (sccoda_sampler::reject_conc_above)
 };
 
 // is parameter i one of the frozen ones (sigma_d, ind_raw) of a run with Dims::freeze?
@@ -614,7 +615,8 @@ __device__ __noinline__ double dm_value(const Dims& dm, const DataTile<T>& dt, c
     // Guard (documented deviation): beyond c_max the lgamma differences have lost all
     // precision (the reference's fp64 graph then evaluates to the bare multinomial constant, a spurious mode
     // thousands of nats above the posterior that traps the chain); such states get a NaN value => rejected.
-    const T c_max = sizeof(T) == 4 ? T(1e6) : T(1e15);
+    // The limit is sccoda_sampler::reject_conc_above (default 1e6 in fp32, 1e15 in fp64; infinity switches the guard off).
+    const T c_max = (T)dm.conc_max;
     // fp32: concentrations >= c_joint switch to the joint (cancellation-free) form, which already contains
     // -lgamma(c); never taken in the fp64 build
     const T c_joint = sizeof(T) == 4 ? T(SCCODA_C_JOINT) : T(SCCODA_C_JOINT_F64);

@@ -75,8 +75,12 @@ class DeviceProblem:
         return cls(pack(x, y, ref, dtype=dtype, grouped=grouped), chains, device)
 
     # ------------------------------------------------------------------ K1
-    def logp_grad(self, theta):
-        """theta [B,C,P] (device tensor or array) -> (logp [B,C] f64, grad [B,C,P])."""
+    def logp_grad(self, theta, kernel_kind: Optional[int] = None, reject_conc_above: float = 0.0):
+        """theta [B,C,P] (device tensor or array) -> (logp [B,C] f64, grad [B,C,P]).
+
+        kernel_kind (as reported by `sccoda_kernel_kind` / SampleOutput.kernel_kind): evaluate through the device
+        functions of that sampler kernel family — 3 / 4 the case/control kernels, 5 / 6 the multi-group kernels —
+        instead of the generic ones (`sccoda_logp_grad_as`)."""
         torch = _torch()
         theta = torch.as_tensor(theta, dtype=self.tdtype, device=self.device).contiguous()
         assert tuple(theta.shape) == (self.B, self.C, self.P), theta.shape
@@ -84,8 +88,13 @@ class DeviceProblem:
         grad = torch.empty_like(theta)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            nat.check(nat.lib().sccoda_logp_grad(ctypes.byref(self.c_problem), _ptr(theta), _ptr(logp), _ptr(grad),
-                                                 stream), "sccoda_logp_grad")
+            if kernel_kind is None and reject_conc_above == 0.0:
+                nat.check(nat.lib().sccoda_logp_grad(ctypes.byref(self.c_problem), _ptr(theta), _ptr(logp), _ptr(grad),
+                                                     stream), "sccoda_logp_grad")
+            else:
+                nat.check(nat.lib().sccoda_logp_grad_as(ctypes.byref(self.c_problem), int(kernel_kind or 0),
+                                                        float(reject_conc_above), _ptr(theta), _ptr(logp), _ptr(grad),
+                                                        stream), "sccoda_logp_grad_as")
         return logp, grad
 
     # ------------------------------------------------------------------ K2/K3
@@ -93,14 +102,15 @@ class DeviceProblem:
                      num_leapfrog: int = 10, max_tree_depth: int = 10, step_size: float = 0.01,
                      target_accept: float = 0.75, seed: int = 0, chain_id0: int = 0,
                      warps_per_chain: int = 0, chains_per_cta: int = 0, generic_only: bool = False,
-                     freeze_spike_slab: bool = False) -> nat.Sampler:
+                     freeze_spike_slab: bool = False, reject_conc_above: float = 0.0) -> nat.Sampler:
         if num_adapt is None:
             num_adapt = int(0.8 * num_burnin)            # scCODA_model.py:284-285
         return nat.Sampler(method=method, num_results=num_results, num_burnin=num_burnin, num_adapt=num_adapt,
                            num_leapfrog=num_leapfrog, max_tree_depth=max_tree_depth, step_begin=0, step_end=0,
                            step_size=step_size, target_accept=target_accept, seed=seed, chain_id0=chain_id0,
                            warps_per_chain=warps_per_chain, store_draws=1, chains_per_cta=chains_per_cta,
-                           generic_only=int(bool(generic_only)), freeze_spike_slab=int(bool(freeze_spike_slab)))
+                           generic_only=int(bool(generic_only)), freeze_spike_slab=int(bool(freeze_spike_slab)),
+                           reject_conc_above=float(reject_conc_above))
 
     def plan(self, smp: nat.Sampler):
         w, c, g, s = (ctypes.c_int32() for _ in range(4))
@@ -197,6 +207,34 @@ class DeviceProblem:
                                   "last_step_size")):
             out[name] = summ[..., o + i]
         return out
+
+
+def sample_raw_host(x, y, ref, chains: int, init: np.ndarray, smp: nat.Sampler, dtype=np.float32, want_draws: bool = True,
+                    want_summary: bool = False, summary_skip: int = 0, device: int = 0):
+    """The whole path from RAW host arrays through `sccoda_sample_raw_host`: packing (C++), H2D, sampler, summaries,
+    D2H, all inside the native call.  x [B,N,D], y [B,N,K] float64, ref [B].  Returns (draws, stats, summary, timings)
+    with timings = dict(pack_ms, kernel_ms, total_ms)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    B, N, K = y.shape
+    D = x.shape[2]
+    assert x.shape[:2] == (B, N)
+    ref = np.ascontiguousarray(np.broadcast_to(np.asarray(ref, dtype=np.int32), (B,)))
+    dt = np.dtype(dtype)
+    C, S, P = int(chains), smp.num_results, D + 2 * D * (K - 1) + K
+    init = np.ascontiguousarray(init, dtype=dt)
+    assert init.shape == (B, C, P)
+    draws = np.empty((B, C, S, P), dtype=dt) if want_draws else None
+    stats = np.empty((B, C, S, nat.NSTAT), dtype=dt) if want_draws else None
+    width = nat.NSUM_PARAM * P + nat.NSUM_BETA * D * K + nat.NSUM_SCALAR
+    summ = np.empty((B, C, width), dtype=np.float64) if want_summary else None
+    tm = (ctypes.c_float * 3)()
+    nat.check(nat.lib().sccoda_sample_raw_host(
+        B, N, K, D, C, x.ctypes.data, y.ctypes.data, ref.ctypes.data, nat.F32 if dt.itemsize == 4 else nat.F64,
+        ctypes.byref(smp), init.ctypes.data, draws.ctypes.data if draws is not None else None,
+        stats.ctypes.data if stats is not None else None, summ.ctypes.data if summ is not None else None,
+        int(summary_skip), int(device), tm), "sccoda_sample_raw_host")
+    return draws, stats, summ, {"pack_ms": float(tm[0]), "kernel_ms": float(tm[1]), "total_ms": float(tm[2])}
 
 
 def sample_host(packed: PackedProblem, chains: int, init: np.ndarray, smp: nat.Sampler, want_draws: bool = True,

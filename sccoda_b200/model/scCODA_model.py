@@ -4,8 +4,13 @@ Dirichlet-multinomial spike-and-slab model with a reference cell type — host-s
 
 Same class names, constructor arguments, sampler methods, defaults and result contents as the reference; the
 TensorFlow-Probability machinery behind `sampling()` is replaced by the persistent sm_100a kernels of
-`sccoda_b200.engine` (no TensorFlow, no CPU fallback).  New optional keyword arguments (`num_chains`, `seed`,
-`dtype`, `device`) default to the reference behaviour: one chain, fp32 device arithmetic.
+`sccoda_b200.engine` (no TensorFlow, no CPU fallback).  New optional keyword arguments of the sampler methods:
+`num_chains` (default 1, as the reference), `seed`, `device`, `dtype` (default float32 — the reference computes in
+float64; `dtype=np.float64` selects the fp64 build of the kernels) and `reject_conc_above`: states with a
+concentration exp(alpha_k + x.beta_k) above this limit are rejected (default 1e6 in fp32, 1e15 in fp64 — beyond
+that the reference's own float64 differences lgamma(c+y) - lgamma(c) have no correct digit left and evaluate to the
+bare multinomial constant, a spurious mode; `reject_conc_above=np.inf` with `dtype=np.float64` reproduces the
+reference's arithmetic including that mode).
 
 The model (scCODA_model.py:646-658):
     y | x      ~ DirichletMultinomial(concentration = exp(alpha + x beta), total = sum_k y)
@@ -85,7 +90,7 @@ class CompositionalModel:
 
         kernel
             dict describing the transition kernel: method ("hmc" | "hmc_da" | "nuts"), step_size, num_leapfrog_steps,
-            max_tree_depth, num_adapt_steps, num_chains, seed, dtype, device, verbose.
+            max_tree_depth, num_adapt_steps, num_chains, seed, dtype, device, verbose, reject_conc_above.
         init_state
             list of the four state parts (one chain) or an array [num_chains, P].
         trace_fn
@@ -111,7 +116,9 @@ class CompositionalModel:
         smp = prob.make_sampler(method, int(num_results), int(num_burnin), kernel.get("num_adapt_steps"),
                                 int(kernel.get("num_leapfrog_steps", 10)), int(kernel.get("max_tree_depth", 10)),
                                 float(kernel.get("step_size", 0.01)), float(kernel.get("target_accept_prob", 0.75)),
-                                seed=int(seed), freeze_spike_slab=bool(kernel.get("freeze_spike_slab", False)))
+                                seed=int(seed), freeze_spike_slab=bool(kernel.get("freeze_spike_slab", False)),
+                                reject_conc_above=-1.0 if np.isinf(kernel.get("reject_conc_above", 0.0))
+                                else float(kernel.get("reject_conc_above", 0.0)))
         total = num_burnin + num_results
         verbose = bool(kernel.get("verbose", False))
         progress, chunk = None, None
@@ -161,12 +168,14 @@ class CompositionalModel:
         return states_burnin, stats, p_accept
 
     def _run(self, method: str, num_results, num_burnin, num_adapt_steps, step_size, verbose, trace_keys,
-             num_leapfrog_steps=10, max_tree_depth=10, num_chains=1, seed=None, dtype=np.float32, device=None):
+             num_leapfrog_steps=10, max_tree_depth=10, num_chains=1, seed=None, dtype=np.float32, device=None,
+             reject_conc_above=0.0):
         if num_adapt_steps is None:
             num_adapt_steps = int(0.8 * num_burnin)                              # scCODA_model.py:284-285
         kernel = dict(method=method, step_size=step_size, num_leapfrog_steps=num_leapfrog_steps,
                       max_tree_depth=max_tree_depth, num_adapt_steps=num_adapt_steps, target_accept_prob=0.75,
-                      num_chains=num_chains, seed=seed, dtype=dtype, device=device, verbose=verbose)
+                      num_chains=num_chains, seed=seed, dtype=dtype, device=device, verbose=verbose,
+                      reject_conc_above=reject_conc_above)
         init = self.init_params if num_chains == 1 else self.init_states(num_chains)
         states, kernel_results, duration = self.sampling(
             num_results, num_burnin, kernel, init, trace_fn=lambda kr: {new: kr[old] for new, old in trace_keys})

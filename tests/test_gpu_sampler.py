@@ -609,6 +609,27 @@ def test_host_buffer_entry_point_matches_device_path():
     assert np.array_equal(summ, summ_dev)
 
 
+def test_raw_host_entry_point_packs_and_matches_device_path():
+    """sccoda_sample_raw_host (raw x / y host arrays: packer + copies + sampler + summaries inside one native call) ==
+    packing in Python and sampling through the device-pointer path, bit for bit."""
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem, sample_raw_host
+    xs, ys = zip(*[synthetic_dataset(60 + b, N=20, K=20) for b in range(3)])
+    xs, ys = np.stack(xs), np.stack(ys)
+    ys[1, 3, 2] = 0                                                          # pseudocount inside the native packer
+    refs = np.array([19, 0, 7], dtype=np.int32)
+    init = np.stack([_init(np.random.RandomState(3 + b), 1, 20, 4) for b in range(3)]).astype(np.float32)
+    prob = DeviceProblem(pack(xs, ys, refs, dtype=np.float32), chains=4)
+    out = prob.sample(init, prob.make_sampler(0, 150, 50, seed=23))
+    summ_dev = prob.summarize(out.draws, out.stats, 50).cpu().numpy()
+    draws, stats, summ, tm = sample_raw_host(xs, ys, refs, 4, init, prob.make_sampler(0, 150, 50, seed=23),
+                                             want_draws=True, want_summary=True, summary_skip=50)
+    assert tm["kernel_ms"] > 0 and tm["pack_ms"] > 0 and tm["total_ms"] >= tm["pack_ms"]
+    assert np.array_equal(draws, out.draws.cpu().numpy())
+    assert np.array_equal(stats, out.stats.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(summ, summ_dev)
+
+
 def test_diverging_flag_and_negative_sigma_rejection():
     """A huge step size throws proposals into sigma_d < 0 / overflow: they must be rejected, flagged and finite."""
     from sccoda_b200.engine import DeviceProblem

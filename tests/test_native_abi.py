@@ -47,7 +47,7 @@ def _problem(pk, C):
 def _sampler(**kw):
     d = dict(method=0, num_results=100, num_burnin=50, num_adapt=40, num_leapfrog=10, max_tree_depth=10, step_begin=0,
              step_end=0, step_size=0.01, target_accept=0.75, seed=1, chain_id0=0, warps_per_chain=0, store_draws=1,
-             chains_per_cta=0, generic_only=0, freeze_spike_slab=0)
+             chains_per_cta=0, generic_only=0, freeze_spike_slab=0, reject_conc_above=0.0)
     d.update(kw)
     return nat.Sampler(**d)
 
