@@ -136,7 +136,7 @@ __device__ __forceinline__ float warp_sum1(float v) {
 // Staging: the packed dataset (include/sccoda_b200.h) re-laid lane-major into shared memory (CcPlan, kernels.h)
 // ------------------------------------------------------------------------------------------------
 struct CcTile {
-    uint32_t cf, yv, ov, rows, el;   // shared-memory byte offsets (CcPlan)
+    uint32_t cf, yv, ov, om, rows, el;   // shared-memory byte offsets (CcPlan)
     int NT, NOT;                     // items / odd counts of the fullest pair of THIS dataset (loop bounds)
     int N, NK, nbig;
     float cnt0, cnt1;                // rows of the two covariate groups
@@ -158,7 +158,8 @@ __device__ __forceinline__ void cc_pair_to_col(int p, int K, int& u, int& col) {
 __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl, CcTile& t) {
     using T = float;
     const int N = a.dm.N, K = a.dm.K, NK = a.dm.NK, NP = 2 * (K + 1);
-    t.cf = (uint32_t)pl.cf; t.yv = (uint32_t)pl.yv; t.ov = (uint32_t)pl.ov; t.rows = (uint32_t)pl.rows; t.el = (uint32_t)pl.el;
+    t.cf = (uint32_t)pl.cf; t.yv = (uint32_t)pl.yv; t.ov = (uint32_t)pl.ov; t.om = (uint32_t)pl.om;
+    t.rows = (uint32_t)pl.rows; t.el = (uint32_t)pl.el;
     t.N = N; t.NK = NK;
     t.c_max = (float)a.dm.conc_max;
     // [0]: items, [1]: odd counts of the fullest pair of this dataset, [2]: elements with a count >= 6
@@ -170,6 +171,9 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
     float* cf = sp<float>(t.cf);
     float* yv = sp<float>(t.yv);
     float* ov = sp<float>((uint32_t)pl.ov);
+    float* om = sp<float>((uint32_t)pl.om);
+    int* fill = sp<int>((uint32_t)pl.fill);
+    if (threadIdx.x < 64) fill[threadIdx.x] = 0;
     const T* pcoef = static_cast<const T*>(a.pcoef) + (size_t)b * NP * 6;
     // rational coefficients: cf[j][lane] = (pair (0,lane), pair (1,lane)); lane K = row totals; lanes > K: zero
     for (int i = threadIdx.x; i < 6 * 32 * 2; i += blockDim.x) {
@@ -178,9 +182,13 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
         if (lane <= K) v = pcoef[(lane < K ? u * K + lane : 2 * K + u) * 6 + j];
         cf[i] = v;
     }
-    // item and odd counts: padding is the count 6, which contributes psi(c+6) - psi(c+6) = 0
-    for (int i = threadIdx.x; i < a.NT * kItemR * 64; i += blockDim.x) yv[i] = 6.0f;
-    for (int i = threadIdx.x; i < a.NOT * 64; i += blockDim.x) ov[i] = 6.0f;
+    // item counts: padding is the count 6, which contributes psi(c+6) - psi(c+6) = 0; odd counts: padding has the
+    // multiplicity 0
+    for (int i = threadIdx.x; i < pl.NTC * kItemR * 64; i += blockDim.x) yv[i] = 6.0f;
+    for (int i = threadIdx.x; i < a.NOT * 64; i += blockDim.x) {
+        ov[i] = 1.0f;
+        om[i] = 0.0f;
+    }
     __syncthreads();
     const T* iy = static_cast<const T*>(a.iy) + (size_t)b * kItemR * a.NImax;
     const uint16_t* ipair = a.ipair + (size_t)b * a.NImax;
@@ -192,16 +200,39 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
         int u, col;
         cc_pair_to_col(p, K, u, col);
         yv[((tt * kItemR + j) * 32 + col) * 2 + u] = iy[j * a.NImax + it];
-        if (j == 0) atomicMax(&bounds[0], tt + 1);
+        if (j == 0) {
+            atomicMax(&bounds[0], tt + 1);
+            atomicMax(&fill[col * 2 + u], tt * kItemR + (int)a.inreal[(size_t)b * a.NImax + it]);   // data counts of the pair
+        }
     }
+    __syncthreads();
+    // Odd counts y (below 6, not in {0..5}: the 0.5 pseudocount, non-integer data):
+    //   psi(c + y) - psi(c + 6) = [psi(c + y + 6) - psi(c + 6)] - sum_{i<6} 1/(c + y + i)
+    // The bracket has the form of an item count, so y + 6 goes into the next free item slot of the pair (usually
+    // padding of its last item: no extra work); the sum is a rational in c + y, evaluated once per DISTINCT odd value
+    // of the pair and weighted with how often it occurs (ov / om; cc_grad).
     const int NG = a.NG[b];
     const T* oy = static_cast<const T*>(a.oy) + (size_t)b * a.NOmax;
     for (int q = threadIdx.x; q < NG; q += blockDim.x) {
         const uint32_t od = a.odesc[(size_t)b * a.NGmax + q];
         int u, col;
         cc_pair_to_col(a.opair[(size_t)b * a.NGmax + q], K, u, col);
-        for (int tt = 0; tt < (int)(od >> 16); ++tt) ov[(tt * 32 + col) * 2 + u] = oy[(od & 0xffffu) + tt];
-        atomicMax(&bounds[1], (int)(od >> 16));
+        const int base = fill[col * 2 + u], n = (int)(od >> 16);
+        int nd = 0;
+        for (int tt = 0; tt < n; ++tt) {
+            const float y = oy[(od & 0xffffu) + tt];
+            const int slot = base + tt;
+            yv[(slot * 32 + col) * 2 + u] = y + 6.0f;            // slot = item * R + position
+            int d = 0;
+            while (d < nd && ov[(d * 32 + col) * 2 + u] != y) ++d;
+            if (d == nd) {
+                ov[(d * 32 + col) * 2 + u] = y;
+                ++nd;
+            }
+            om[(d * 32 + col) * 2 + u] += 1.0f;
+        }
+        if (n > 0) atomicMax(&bounds[0], (base + n - 1) / kItemR + 1);
+        atomicMax(&bounds[1], nd);
     }
     // value pass, rows: (total n, r(n) or lgamma(n) as in _pack.py's eycst, group); the row terms are evaluated as
     // -[lgamma(S+n) - lgamma(S) - lgamma(n)] in fp32 (cancellation-free), so sum_n lgamma(n) moves into the constant
@@ -284,6 +315,15 @@ __device__ __forceinline__ f32x2 pair_rational2(f32x2 c, const f32x2* __restrict
     return mul2(num, rcp2(mul2(a, a46)));
 }
 
+// -sum_{i<6} 1/(z + i) = -(2z + 5) [1/a + 1/(a+4) + 1/(a+6)], a = z (z + 5), with one reciprocal
+__device__ __forceinline__ f32x2 r6_neg2(f32x2 z) {
+    const f32x2 a = mul2(z, add2(z, dup2(5.0f)));
+    const f32x2 a4 = add2(a, dup2(4.0f)), a6 = add2(a, dup2(6.0f));
+    const f32x2 a46 = mul2(a4, a6);
+    const f32x2 num = fma2(a, add2(a4, a6), a46);
+    return mul2(mul2(fma2(dup2(-2.0f), z, dup2(-5.0f)), num), rcp2(mul2(a, a46)));
+}
+
 // Two items at once: sum_j [psi(c + y_j) - psi(c + 6)] for the R = 5 counts of each (all >= 6), with the midpoint
 // expansion at x_j = c + y_j - 1/2 (cm = c - 1/2); a = w^5 and nb = -5 (psi(x+1/2) - ln x) at x = c + 5.5, w = 1/x
 // refer the log-product and the series to c + 6 (cf. PairRec / item_eval in grouped.cuh).
@@ -335,14 +375,12 @@ __device__ __forceinline__ CcGrad cc_grad(const CcTile& t, const CcLane& ln, con
     const f32x2* yv = sp<f32x2>(t.yv) + lane;
 #pragma unroll 1
     for (int tt = 0; tt < t.NT; ++tt, yv += SCCODA_ITEM_R * 32) br = add2(br, item_eval2(cm, a5, nb, yv));
+    // odd counts: their shifted values sit in the items above; what is left is -m sum_{i<6} 1/(c + y + i) per distinct
+    // odd value y of the pair (m = its multiplicity; cc_stage)
     yv = sp<f32x2>(t.ov) + lane;
-    if (t.NOT > 0) {
-        // counts below 6 that are not in {0..5} (the 0.5 pseudocount, non-integer data): psi(c+y) - psi(c+6) one by one
-        const f32x2 x6 = add2(c, dup2(5.5f));
-        const f32x2 nref = fma2(lg2_2(x6), dup2(-SCCODA_LN2F), mul2(nb, dup2(1.0f / (float)SCCODA_ITEM_R)));   // -psi(c+6)
+    const f32x2* mv = sp<f32x2>(t.om) + lane;
 #pragma unroll 1
-        for (int tt = 0; tt < t.NOT; ++tt, yv += 32) br = add2(br, add2(psi_any2(add2(c, *yv)), nref));
-    }
+    for (int tt = 0; tt < t.NOT; ++tt, yv += 32, mv += 32) br = fma2(*mv, r6_neg2(add2(c, *yv)), br);
     // d logp / d log c_uk = c_uk (Br_uk - Br_total(u)), chain rule
     const float bt0 = __shfl_sync(0xffffffffu, lo2(br), ln.K), bt1 = __shfl_sync(0xffffffffu, hi2(br), ln.K);
     const float G0 = c0 * (lo2(br) - bt0), G1 = c1 * (hi2(br) - bt1);        // c0 = c1 = 0 on lanes >= K

@@ -18,7 +18,7 @@
 namespace sccoda {
 
 struct MgTile {
-    uint32_t cf, yv, ov, rows, el, xg, cnt, bnd;   // shared-memory byte offsets (MgPlan)
+    uint32_t cf, yv, ov, om, rows, el, xg, cnt, bnd;   // shared-memory byte offsets (MgPlan)
     uint32_t yv_stride, ov_stride;                 // bytes per (pair of groups, column slot)
     int UP, UPmax;                                 // pairs of groups of THIS dataset / of the fullest dataset of the batch
     int N, NK, nbig;
@@ -48,11 +48,13 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
 __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl, int UPmax, int NS, MgTile& t) {
     using T = float;
     const int N = a.dm.N, K = a.dm.K, D = a.dm.D, NK = a.dm.NK, Umax = a.Umax, NP = Umax * (K + 1);
-    const int NT = a.NT, NOT = a.NOT;
+    const int NOT = a.NOT;
     t.cf = pin_u32((uint32_t)pl.cf); t.yv = pin_u32((uint32_t)pl.yv); t.ov = pin_u32((uint32_t)pl.ov);
+    t.om = pin_u32((uint32_t)pl.om);
     t.rows = pin_u32((uint32_t)pl.rows); t.el = pin_u32((uint32_t)pl.el); t.xg = pin_u32((uint32_t)pl.xg);
     t.cnt = pin_u32((uint32_t)pl.cnt); t.bnd = pin_u32((uint32_t)pl.bounds);
-    t.yv_stride = pin_u32((uint32_t)(NT * kItemR * 32 * 8)); t.ov_stride = pin_u32((uint32_t)(NOT * 32 * 8));
+    const int NTC = pl.NTC;
+    t.yv_stride = pin_u32((uint32_t)(NTC * kItemR * 32 * 8)); t.ov_stride = pin_u32((uint32_t)(NOT * 32 * 8));
     t.N = N; t.NK = NK;
     t.c_max = (float)a.dm.conc_max;
     t.UP = (a.U[b] + 1) >> 1;
@@ -78,6 +80,9 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
     float* cf = sp<float>((uint32_t)pl.cf);
     float* yv = sp<float>((uint32_t)pl.yv);
     float* ov = sp<float>((uint32_t)pl.ov);
+    float* om = sp<float>((uint32_t)pl.om);
+    int* fill = sp<int>((uint32_t)pl.fill);
+    for (int i = threadIdx.x; i < NQ * 64; i += blockDim.x) fill[i] = 0;
     const T* pcoef = static_cast<const T*>(a.pcoef) + (size_t)b * NP * 6;
     // rational coefficients: cf[q][j][lane] = (pair (2 up, col), pair (2 up + 1, col)), col = 32 s + lane; col K = row totals
     for (int i = threadIdx.x; i < NQ * 6 * 32 * 2; i += blockDim.x) {
@@ -87,9 +92,13 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
         if (col <= K && u < Umax) v = pcoef[(col < K ? u * K + col : Umax * K + u) * 6 + j];
         cf[i] = v;
     }
-    // item and odd counts: padding is the count 6, which contributes psi(c+6) - psi(c+6) = 0
-    for (int i = threadIdx.x; i < NQ * NT * kItemR * 64; i += blockDim.x) yv[i] = 6.0f;
-    for (int i = threadIdx.x; i < NQ * NOT * 64; i += blockDim.x) ov[i] = 6.0f;
+    // item counts: padding is the count 6, which contributes psi(c+6) - psi(c+6) = 0; odd counts: padding has the
+    // multiplicity 0
+    for (int i = threadIdx.x; i < NQ * NTC * kItemR * 64; i += blockDim.x) yv[i] = 6.0f;
+    for (int i = threadIdx.x; i < NQ * NOT * 64; i += blockDim.x) {
+        ov[i] = 1.0f;
+        om[i] = 0.0f;
+    }
     __syncthreads();
     const T* iy = static_cast<const T*>(a.iy) + (size_t)b * kItemR * a.NImax;
     const uint16_t* ipair = a.ipair + (size_t)b * a.NImax;
@@ -101,18 +110,38 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
         int u, col;
         mg_pair_to_col(p, K, Umax, u, col);
         const int q = (u >> 1) * NS + (col >> 5);
-        yv[(((q * NT + tt) * kItemR + j) * 32 + (col & 31)) * 2 + (u & 1)] = iy[j * a.NImax + it];
-        if (j == 0) atomicMax(&bounds[q], tt + 1);
+        yv[(((q * NTC + tt) * kItemR + j) * 32 + (col & 31)) * 2 + (u & 1)] = iy[j * a.NImax + it];
+        if (j == 0) {
+            atomicMax(&bounds[q], tt + 1);
+            atomicMax(&fill[(q * 32 + (col & 31)) * 2 + (u & 1)], tt * kItemR + (int)a.inreal[(size_t)b * a.NImax + it]);
+        }
     }
+    __syncthreads();
+    // odd counts: y + 6 into the next free item slots of the pair, -m sum_{i<6} 1/(c + y + i) per distinct value y
+    // (cc_stage in hmc_cc.cuh explains the identity)
     const int NG = a.NG[b];
     const T* oy = static_cast<const T*>(a.oy) + (size_t)b * a.NOmax;
     for (int q = threadIdx.x; q < NG; q += blockDim.x) {
         const uint32_t od = a.odesc[(size_t)b * a.NGmax + q];
         int u, col;
         mg_pair_to_col(a.opair[(size_t)b * a.NGmax + q], K, Umax, u, col);
-        const int qq = (u >> 1) * NS + (col >> 5);
-        for (int tt = 0; tt < (int)(od >> 16); ++tt) ov[((qq * NOT + tt) * 32 + (col & 31)) * 2 + (u & 1)] = oy[(od & 0xffffu) + tt];
-        atomicMax(&bounds[NQ + qq], (int)(od >> 16));
+        const int qq = (u >> 1) * NS + (col >> 5), cl = col & 31, h = u & 1;
+        const int base = fill[(qq * 32 + cl) * 2 + h], n = (int)(od >> 16);
+        int nd = 0;
+        for (int tt = 0; tt < n; ++tt) {
+            const float y = oy[(od & 0xffffu) + tt];
+            const int slot = base + tt;                          // item * R + position
+            yv[((qq * NTC * kItemR + slot) * 32 + cl) * 2 + h] = y + 6.0f;
+            int d = 0;
+            while (d < nd && ov[((qq * NOT + d) * 32 + cl) * 2 + h] != y) ++d;
+            if (d == nd) {
+                ov[((qq * NOT + d) * 32 + cl) * 2 + h] = y;
+                ++nd;
+            }
+            om[((qq * NOT + d) * 32 + cl) * 2 + h] += 1.0f;
+        }
+        if (n > 0) atomicMax(&bounds[qq], (base + n - 1) / kItemR + 1);
+        atomicMax(&bounds[NQ + qq], nd);
     }
     // value pass, rows and elements: as in cc_stage (hmc_cc.cuh), concentration slot = group * CS + column
     float4* rows = sp<float4>((uint32_t)pl.rows);
@@ -230,6 +259,7 @@ __device__ __forceinline__ MgVec<D, NS> mg_grad(const MgTile& t, const MgLane<NS
         }
     }
     uint32_t cf_off = t.cf + lane * 8, yv_off = t.yv + lane * 8, ov_off = t.ov + lane * 8, xg_off = t.xg;
+    const uint32_t om_delta = t.om - t.ov;
     uint32_t pcw = pc_off + lane * 4;
     const float* cnt = sp<float>(t.cnt);
     const int* bnd = sp<int>(t.bnd);
@@ -273,14 +303,11 @@ __device__ __forceinline__ MgVec<D, NS> mg_grad(const MgTile& t, const MgLane<NS
             const int nt = bnd[up * NS + s], n_odd = bnd[n_q + up * NS + s];
 #pragma unroll 1
             for (int tt = 0; tt < nt; ++tt, yv += SCCODA_ITEM_R * 32) b2 = add2(b2, item_eval2(cm, a5, nb, yv));
-            if (n_odd > 0) {
-                // counts below 6 that are not in {0..5} (the 0.5 pseudocount, non-integer data), one by one
-                const f32x2 x6 = add2(c[s], dup2(5.5f));
-                const f32x2 nref = fma2(lg2_2(x6), dup2(-SCCODA_LN2F), mul2(nb, dup2(1.0f / (float)SCCODA_ITEM_R)));   // -psi(c+6)
-                yv = sp<f32x2>(ov_off);
+            // odd counts: the shifted values sit in the items above; -m sum_{i<6} 1/(c + y + i) per distinct value
+            yv = sp<f32x2>(ov_off);
 #pragma unroll 1
-                for (int tt = 0; tt < n_odd; ++tt, yv += 32) b2 = add2(b2, add2(psi_any2(add2(c[s], *yv)), nref));
-            }
+            for (int tt = 0; tt < n_odd; ++tt, yv += 32)
+                b2 = fma2(*reinterpret_cast<const f32x2*>(reinterpret_cast<const char*>(yv) + om_delta), r6_neg2(add2(c[s], *yv)), b2);
             br[s] = b2;
             cf_off += 6 * 32 * 8; yv_off += t.yv_stride; ov_off += t.ov_stride;
         }

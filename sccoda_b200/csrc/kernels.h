@@ -114,20 +114,26 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int K, int D, int Umax, int
 
 // Shared-memory plan of the case/control HMC kernel (hmc_cc.cuh): lane-major arrays at compile-time offsets first.
 struct CcPlan {
-    size_t cf, yv, ov, rows, el, bounds, red, data_total;   // per CTA
+    size_t cf, yv, ov, om, rows, el, bounds, red, fill, data_total;   // per CTA
     size_t pc, vec, slots, chain_total;        // per chain (relative)
+    int NTC;                                   // item slots per pair: the packed items plus room for the shifted odd counts
 };
 // n_slots: float4-per-lane vectors of the NUTS tree (0 for HMC)
 __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT, int n_slots) {
     CcPlan p;
+    // odd counts (the 0.5 pseudocount, non-integer data) are staged as counts y + 6 in the item slots of their pair
+    // (hmc_cc.cuh: cc_stage); the padding of the last packed item takes them, at worst ceil(NOT / R) more items
+    p.NTC = NT + (NOT + kItemR - 1) / kItemR;
     size_t o = 0;
     p.cf = o; o += 6 * 32 * 8;                                   // f32x2[6][32] rational coefficients (group 0, group 1)
-    p.yv = o; o += (size_t)NT * kItemR * 32 * 8;                 // f32x2[NT][R][32] item counts
-    p.ov = o; o += (size_t)NOT * 32 * 8;                         // f32x2[NOT][32] odd counts (directly after the items)
+    p.yv = o; o += (size_t)p.NTC * kItemR * 32 * 8;              // f32x2[NTC][R][32] item counts
+    p.ov = o; o += (size_t)NOT * 32 * 8;                         // f32x2[NOT][32] distinct odd counts of a pair ...
+    p.om = o; o += (size_t)NOT * 32 * 8;                         // f32x2[NOT][32] ... and how often each occurs
     p.rows = o; o += (size_t)N * 16;                             // (row total, host-like constant, group, -)
     p.el = o; o += (size_t)N * K * 16;                           // (count, host constant, concentration slot, -)
     p.bounds = o; o += 16;                                       // int[3]: per-dataset loop bounds (items, odd counts, big elements)
     p.red = o; o += 32;                                          // double[4]: staging reduction
+    p.fill = o; o += 64 * 4;                                     // int[32][2]: data counts in the item slots of every pair
     p.data_total = o;
     p.pc = 0;                                                    // float[64] concentrations, slot u*32 + column
     p.vec = 256;                                                 // float[96] flat state vector
@@ -140,8 +146,9 @@ __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT, int n_s
 // column slot) — UP = pairs of groups of the fullest dataset, NS = cell types per lane (1: K <= 31, 2: K <= 62) —
 // plus the covariate values and row counts of the groups.
 struct MgPlan {
-    size_t cf, yv, ov, rows, el, xg, cnt, bounds, red, data_total;   // per CTA
+    size_t cf, yv, ov, om, rows, el, xg, cnt, bounds, red, fill, data_total;   // per CTA
     size_t pc, vec, slots, chain_total;                               // per chain (relative)
+    int NTC;                                                          // item slots per pair incl. room for the shifted odd counts (CcPlan)
 };
 constexpr int kMgMaxGroups = 32, kMgMaxD = 4, kMgMaxK = 62, kMgMaxD2 = 3 /* largest D with two cell types per lane */;
 // float4 per lane of one stored state vector: NS (alpha + D b_offset + D ind_raw) + D sigma
@@ -150,16 +157,19 @@ __host__ __device__ constexpr int mg_vec_quads(int D, int NS) { return (NS * (1 
 __host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NS, int NT, int NOT, int n_slots) {
     MgPlan p;
     const size_t Q = (size_t)UP * NS;
+    p.NTC = NT + (NOT + kItemR - 1) / kItemR;
     size_t o = 0;
     p.cf = o; o += Q * 6 * 32 * 8;                               // f32x2[UP][NS][6][32] rational coefficients
-    p.yv = o; o += Q * NT * kItemR * 32 * 8;                     // f32x2[UP][NS][NT][R][32] item counts
-    p.ov = o; o += Q * NOT * 32 * 8;                             // f32x2[UP][NS][NOT][32] odd counts
+    p.yv = o; o += Q * p.NTC * kItemR * 32 * 8;                  // f32x2[UP][NS][NTC][R][32] item counts
+    p.ov = o; o += Q * NOT * 32 * 8;                             // f32x2[UP][NS][NOT][32] distinct odd counts of a pair ...
+    p.om = o; o += Q * NOT * 32 * 8;                             // f32x2[UP][NS][NOT][32] ... and how often each occurs
     p.rows = o; o += (size_t)N * 16;                             // (row total, host-like constant, slot of S_u, -)
     p.el = o; o += (size_t)N * K * 16;                           // (count, host constant, concentration slot, 1/count)
     p.xg = o; o += rnd16((size_t)UP * D * 8);                    // f32x2[UP][D] covariate values of the groups
     p.cnt = o; o += rnd16((size_t)UP * 2 * 4);                   // float[2 UP] rows per group
     p.bounds = o; o += rnd16((size_t)(2 * Q + 1) * 4);           // int: items / odd counts per (group pair, slot), big elements
     p.red = o; o += 32;                                          // double[4]: staging reduction
+    p.fill = o; o += Q * 64 * 4;                                 // int[UP][NS][32][2]: data counts in the item slots of every pair
     p.data_total = o;
     const size_t P = (size_t)D + 2 * (size_t)D * (K - 1) + K;
     p.pc = 0;                                                    // float[2 UP][32 NS] concentrations, slot u*32*NS + column

@@ -42,6 +42,14 @@ class SampleOutput:
     smem_bytes: int
     launches: int
     kernel_kind: int = 0   # 1 generic HMC, 2 NUTS, 3 / 4 case/control HMC / NUTS, 5 multi-group HMC (include/sccoda_b200.h: sccoda_kernel_kind)
+    events: "object" = None  # (start, end) CUDA events of the launch(es) when sample(sync=False) left kernel_ms open
+
+    def elapsed_ms(self) -> float:
+        """Device time of the sampling launch(es); synchronises on the end event when sample() did not."""
+        if self.kernel_ms is None:
+            self.events[1].synchronize()
+            self.kernel_ms = self.events[0].elapsed_time(self.events[1])
+        return self.kernel_ms
 
     def stat(self, name: str):
         return self.stats[..., nat.STAT_NAMES.index(name)]
@@ -119,8 +127,9 @@ class DeviceProblem:
         return w.value, c.value, g.value, s.value
 
     def sample(self, init, smp: nat.Sampler, chunk: Optional[int] = None, progress=None,
-               draws=None, stats=None) -> SampleOutput:
-        """Run the whole chain (one persistent launch, or `chunk`-step launches with resume through `carry`)."""
+               draws=None, stats=None, sync: bool = True) -> SampleOutput:
+        """Run the whole chain (one persistent launch, or `chunk`-step launches with resume through `carry`).
+        sync=False returns without waiting for the device (kernel_ms stays open until `elapsed_ms()`)."""
         torch = _torch()
         init = torch.as_tensor(init, dtype=self.tdtype, device=self.device).contiguous()
         assert tuple(init.shape) == (self.B, self.C, self.P), (init.shape, (self.B, self.C, self.P))
@@ -154,11 +163,14 @@ class DeviceProblem:
                     stream.synchronize()
                     progress(end, total)
             e1.record(stream)
-            e1.synchronize()
-            ms = e0.elapsed_time(e1)
+            ms = None
+            if sync:
+                e1.synchronize()
+                ms = e0.elapsed_time(e1)
         smp.step_begin, smp.step_end = 0, 0
         return SampleOutput(draws=draws, stats=stats, carry=carry, kernel_ms=ms, warps_per_chain=w,
-                            chains_per_cta=cpc, grid=grid, smem_bytes=smem, launches=launches, kernel_kind=kind.value)
+                            chains_per_cta=cpc, grid=grid, smem_bytes=smem, launches=launches, kernel_kind=kind.value,
+                            events=(e0, e1))
 
     # ------------------------------------------------------------------ K4
     def summary_width(self) -> int:
