@@ -88,6 +88,19 @@ def test_multi_chain_fp64_and_target_log_prob(data_salm):
     assert result.effect_df.shape[0] == 8 and result.intercept_df.shape[0] == 8
 
 
+def test_tutorial_intercepts_and_inclusion_probabilities_through_the_api(data_salm):
+    """The reference-produced numbers of the tutorials (tests/test_oracle_statistical.py: tutorial_pins) through the
+    drop-in API on the device: Haber Salmonella, reference Goblet, sample_hmc() defaults, 64 chains."""
+    from test_oracle_statistical import tutorial_pins
+    model = mod.CompositionalAnalysis(data_salm, formula="Condition", reference_cell_type="Goblet")
+    result = model.sample_hmc(num_chains=64, seed=11, verbose=False)
+    alpha = np.asarray(result.posterior["alpha"])                             # [64, 15000, 8]
+    beta = np.asarray(result.posterior["beta"])                               # [64, 15000, 1, 8]
+    assert alpha.shape == (64, 15000, 8) and beta.shape == (64, 15000, 1, 8)
+    tutorial_pins(alpha.mean(1), (np.abs(beta[:, :, 0, :]) > 1e-3).mean(1))
+    assert 0.45 < result.sampling_stats["acc_rate"] < 0.7
+
+
 def test_sweep_inclusion_probabilities_and_credible_calls_match_oracle():
     """North-star check on sccoda.util.data_generation-style data: posterior inclusion probabilities and
     credible-effect calls of the device sweep (case/control kernel, fp32, 4 chains per dataset) against the fp64 CPU

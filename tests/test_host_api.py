@@ -69,10 +69,56 @@ def test_design_matrix_treatment_coding():
     m, names = design_matrix("Condition + dose+flag", obs)
     assert names == ["Condition[T.H.poly]", "Condition[T.Salm]", "dose", "flag"]
     assert np.array_equal(m[:, 2], obs["dose"]) and np.array_equal(m[:, 3], obs["flag"])
-    with pytest.raises(NotImplementedError):
-        design_matrix("Condition:dose", obs)
     with pytest.raises(KeyError):
         design_matrix("nope", obs)
+
+
+def test_design_matrix_interactions_transforms_and_no_intercept():
+    """The formula language beyond sums of names, with patsy's conventions (column names, term order, the left-most
+    factor of an interaction varying fastest, full-rank coding where the lower-order term is absent)."""
+    obs = pd.DataFrame({"Condition": ["Control", "Control", "Salm", "H.poly", "Salm", "H.poly"],
+                        "Sex": ["f", "m", "f", "m", "m", "f"], "dose": [0.5, 1.0, 2.0, 4.0, 8.0, 16.0],
+                        "age": [1.0, 2.0, 3.0, 4.0, 5.0, 7.0]})
+    cond = {lv: (obs["Condition"] == lv).to_numpy(float) for lv in ("Control", "H.poly", "Salm")}
+    male = (obs["Sex"] == "m").to_numpy(float)
+    # a*b = a + b + a:b; the interaction columns run through the levels of the LEFT factor first
+    m, names = design_matrix("Condition * Sex", obs)
+    assert names == ["Condition[T.H.poly]", "Condition[T.Salm]", "Sex[T.m]", "Condition[T.H.poly]:Sex[T.m]",
+                     "Condition[T.Salm]:Sex[T.m]"]
+    assert np.array_equal(m[:, 3], cond["H.poly"] * male) and np.array_equal(m[:, 4], cond["Salm"] * male)
+    m2, names2 = design_matrix("Condition + Sex + Condition:Sex", obs)
+    assert names2 == names and np.array_equal(m2, m)
+    # categorical x numeric with both margins: treatment coding inside the interaction; numeric terms sort behind
+    m, names = design_matrix("dose + Condition + Condition:dose", obs)
+    assert names == ["Condition[T.H.poly]", "Condition[T.Salm]", "dose", "Condition[T.H.poly]:dose", "Condition[T.Salm]:dose"]
+    assert np.array_equal(m[:, 4], cond["Salm"] * obs["dose"])
+    # ... without the numeric margin every level gets its own slope (full-rank coding)
+    m, names = design_matrix("Condition:dose", obs)
+    assert names == ["Condition[Control]:dose", "Condition[H.poly]:dose", "Condition[Salm]:dose"]
+    assert np.array_equal(m[:, 0], cond["Control"] * obs["dose"])
+    # numeric interactions, powers and removal
+    m, names = design_matrix("(dose + age)**2", obs)
+    assert names == ["dose", "age", "dose:age"] and np.array_equal(m[:, 2], obs["dose"] * obs["age"])
+    m, names = design_matrix("dose*age - dose:age", obs)
+    assert names == ["dose", "age"]
+    # transforms
+    m, names = design_matrix("np.log(dose) + I(age**2 / 2) + center(age) + standardize(dose)", obs)
+    assert names == ["np.log(dose)", "I(age**2 / 2)", "center(age)", "standardize(dose)"]
+    assert np.allclose(m[:, 0], np.log(obs["dose"])) and np.allclose(m[:, 1], obs["age"] ** 2 / 2)
+    assert np.allclose(m[:, 2], obs["age"] - obs["age"].mean())
+    assert np.allclose(m[:, 3], (obs["dose"] - obs["dose"].mean()) / obs["dose"].std(ddof=0))
+    # no intercept: patsy codes the first categorical factor with all its levels; the reference drops column 0 anyway
+    for f in ("0 + Condition", "Condition - 1", "-1 + Condition"):
+        m, names = design_matrix(f, obs)
+        assert names == ["Condition[H.poly]", "Condition[Salm]"]
+        assert np.array_equal(m, np.stack([cond["H.poly"], cond["Salm"]], axis=1))
+    m, names = design_matrix("0 + Condition + Sex", obs)
+    assert names == ["Condition[H.poly]", "Condition[Salm]", "Sex[T.m]"]
+    # two categorical factors interacting without their margins: patsy's mixed coding is not reproduced
+    with pytest.raises(NotImplementedError):
+        design_matrix("Condition:Sex", obs)
+    with pytest.raises(NotImplementedError):
+        design_matrix("C(Condition, Sum)", obs)
 
 
 def test_compositional_analysis_factory():

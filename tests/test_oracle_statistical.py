@@ -34,3 +34,45 @@ def test_oracle_reproduces_reference_end_to_end_assertions():
     # tutorial intercepts for ref=Goblet differ slightly; with ref=TA (5) the alphas must still be ordered alike
     am = draws[0, :, 5000:, -8:].mean((0, 1))
     assert np.argmax(am) == 6 and np.argmin(am) == 7                        # TA.Early largest, Tuft smallest
+
+
+# Reference-produced numbers (captured notebook output of the unmodified reference, the only ones that exist):
+# Haber Salmonella vs control, reference cell type Goblet, sample_hmc() defaults — intercept `Final Parameter`s of
+# tutorials/getting_started.ipynb:449-529 and the inclusion probabilities of summary_extended() in
+# tutorials/Modeling_options_and_result_analysis.ipynb:590-655 (order of the count table; Goblet is the reference).
+TUTORIAL_INTERCEPTS = np.array([1.109, 2.325, 2.508, 1.739, 2.693, 2.104, 2.856, 0.422])
+TUTORIAL_INCLUSION = np.array([0.506933, 1.0, 0.3348, 0.0, 0.398667, 0.418933, 0.267467, 0.417733])
+
+
+def tutorial_pins(alpha_chain_means, inc_chain):
+    """alpha_chain_means [C,K], inc_chain [C,K] (per-chain posterior means / inclusion probabilities, C >= 32 chains).
+    The tutorial numbers are ONE chain of the reference: they must lie inside the spread of single chains, and the
+    many-chain mean of the intercepts within 0.03 of them."""
+    am, asd = alpha_chain_means.mean(0), alpha_chain_means.std(0, ddof=1)
+    assert np.abs(am - TUTORIAL_INTERCEPTS).max() < 0.03, am
+    assert (np.abs(am - TUTORIAL_INTERCEPTS) / asd).max() < 3.0
+    im, isd = inc_chain.mean(0), inc_chain.std(0, ddof=1)
+    assert im[3] == 0.0 and im[1] > 0.99                                      # reference never included, Enterocyte always
+    z = np.abs(im - TUTORIAL_INCLUSION) / np.maximum(isd, 0.01)
+    assert z.max() < 3.0, (im, z)
+    assert np.abs(im - TUTORIAL_INCLUSION).max() < 0.1, im
+    return am, im
+
+
+def test_oracle_matches_tutorial_intercepts_and_inclusion_probabilities():
+    x, y, names = haber_salm()
+    ref = names.index("Goblet")
+    m = o.prepare(x, y, ref)
+    C, K = 64, 8
+    rs = np.random.RandomState(7)
+    init = np.zeros((1, C, m.P))
+    init[..., 0] = 1.0
+    init[..., 1:K] = rs.randn(1, C, K - 1)
+    init[..., -K:] = rs.randn(1, C, K)
+    d, st = c_oracle.sample(m.x[None], m.y[None], m.n_total[None], [m.logp_const], [ref], init, o.METHOD_HMC, 20000, 5000,
+                            seed=2024)
+    dd = d[0, :, 5000:, :]
+    beta = 1.0 / (1.0 + np.exp(-50.0 * dd[..., K:2 * K - 1])) * dd[..., 0:1] * dd[..., 1:K]
+    inc = np.insert((np.abs(beta) > 1e-3).mean(1), ref, 0.0, axis=1)          # result_classes.py:243-251
+    tutorial_pins(dd[..., -K:].mean(1), inc)
+    assert 0.45 < st["is_accepted"].mean() < 0.7                              # tutorials: 49.7 - 60.7 %

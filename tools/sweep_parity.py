@@ -1,6 +1,10 @@
 """Full-length parity of the device sweep against the CPU oracle on generate_sweep data (tools, not product):
 B datasets x 4 chains, sample_hmc(20000, 5000) on both sides with independent random streams; compares posterior
-inclusion probabilities, credible-effect calls, acceptance rates and step sizes.  Writes one JSON object."""
+inclusion probabilities, credible-effect calls, intercepts (alpha) and effects (beta), acceptance rates and step sizes.
+Both sides sample the same target: the oracle runs with the concentration guard of the fp32 kernels (reject_conc_above =
+1e6; --oracle-guard 0 switches it off and the oracle's trapped chains are then counted and left out).  A third run — the
+device in fp64 with the fp64 default guard 1e15 — measures how much posterior mass has a concentration above 1e6.
+Writes one JSON object."""
 import argparse
 import json
 import os
@@ -20,6 +24,8 @@ ap.add_argument("--chains", type=int, default=4)
 ap.add_argument("--K", type=int, default=20)
 ap.add_argument("--results", type=int, default=20000)
 ap.add_argument("--burnin", type=int, default=5000)
+ap.add_argument("--oracle-guard", type=float, default=1e6)
+ap.add_argument("--fp64-datasets", type=int, default=32, help="datasets of the fp64 device run that measures the mass above 1e6")
 ap.add_argument("--conditions", type=int, default=2, help="> 2: one-hot coded conditions (D = conditions - 1), 5 rows each, "
                                                              "one true effect per condition")
 a = ap.parse_args()
@@ -54,7 +60,8 @@ ms = [o.prepare(x[b], y[b], K - 1) for b in range(B)]
 init = sch.initial_states(B, C, D, K, seed=5)
 t0 = time.time()
 d, st_o = c_oracle.sample(np.stack([m.x for m in ms]), np.stack([m.y for m in ms]), np.stack([m.n_total for m in ms]),
-                          [m.logp_const for m in ms], [m.ref for m in ms], init, 0, nr, nb, seed=99)
+                          [m.logp_const for m in ms], [m.ref for m in ms], init, 0, nr, nb, seed=99,
+                          reject_conc_above=a.oracle_guard if a.oracle_guard > 0 else None)
 t_orc = time.time() - t0
 used = d[:, :, nb:, :]
 lp_o = st_o["target_log_prob"][:, :, nb:]
@@ -85,7 +92,49 @@ call_d, call_o = (res["final_effect"] != 0)[keep], (final_o != 0)[keep]
 wt = w_true.reshape(B, D * K)[keep]
 true_mask = wt != 0
 strong_mask = wt >= 1.0
+# intercepts and effects: posterior means pooled over the chains; Monte-Carlo error from the spread of the oracle's
+# chain means.  `Final Parameter` of the intercepts = the 3-decimal rounded mean (result_classes.py:199-206).
+alpha_chain = used[..., -K:].mean(2)                                            # [B,C,K]
+alpha_o = (alpha_chain * sane[:, :, None]).sum(1) / np.maximum(sane.sum(1), 1)[:, None]
+alpha_d = res["mean"][:, -K:]
+se_alpha = float(np.sqrt(np.mean((alpha_chain.var(axis=1, ddof=1) / C)[keep])))
+d_alpha = (alpha_d - alpha_o)[keep]
+beta_chain = beta.mean(2)                                                       # [B,C,D,K-1]
+beta_o = (beta_chain * w4).sum(1) / np.maximum(sane.sum(1), 1)[:, None, None]
+import torch
+beta_d = shard.problem.split_summary(shard.summary)["beta_mean"].mean(1).cpu().numpy().reshape(B, D, K)[:, :, :K1]
+se_beta = float(np.sqrt(np.mean((beta_chain.var(axis=1, ddof=1) / C)[keep])))
+d_beta = (beta_d - beta_o)[keep]
+both_called = ((res["final_effect"] != 0) & (final_o != 0))[keep]
+d_final = (res["final_effect"] - final_o)[keep][both_called]
+
+# posterior mass above the fp32 guard: the device in fp64 (guard 1e15), largest concentration of every retained draw
+nb64 = min(a.fp64_datasets, B)
+cfg64 = sch.SweepConfig(method=0, num_results=nr, num_burnin=nb, chains=C, seed=13, dtype=np.float64)
+res64, shard64 = sch.run_sweep(x[:nb64], y[:nb64], K - 1, cfg64)
+d64 = shard64.out.draws[:, :, nb:, :]                                           # [b,C,S,P] fp64 on the device
+sig64 = d64[..., :D].unsqueeze(-1)
+boff64 = d64[..., D:D + D * K1].reshape(d64.shape[:3] + (D, K1))
+iraw64 = d64[..., D + D * K1:D + 2 * D * K1].reshape(d64.shape[:3] + (D, K1))
+beta64 = torch.sigmoid(50.0 * iraw64) * sig64 * boff64                          # [b,C,S,D,K-1]
+xu = torch.as_tensor(np.unique(x[:nb64].reshape(-1, D), axis=0), device=d64.device)          # distinct covariate rows
+eta = d64[..., -K:].unsqueeze(-2).repeat(1, 1, 1, xu.shape[0], 1)               # [b,C,S,U,K]
+eta[..., :K1] += torch.einsum("ud,bcsdk->bcsuk", xu, beta64)
+max_conc = torch.exp(eta.amax(dim=(-1, -2)))                                    # [b,C,S]
+mass = {"datasets": int(nb64), "draws": int(max_conc.numel()), "kernel_kind": int(shard64.out.kernel_kind),
+        "max_concentration": float(max_conc.max().item()),
+        "share_of_draws_with_a_concentration_above_1e6": float((max_conc > 1e6).double().mean().item()),
+        "share_above_1e4": float((max_conc > 1e4).double().mean().item()),
+        "quantiles_50_99_9999": [float(v) for v in torch.quantile(max_conc.flatten()[::7].double(), torch.tensor([0.5, 0.99, 0.9999], dtype=torch.float64, device=d64.device)).cpu()]}
+
 out = {
+    "alpha_mean_rms_diff": float(np.sqrt(np.mean(d_alpha ** 2))), "alpha_mean_max_abs_diff": float(np.abs(d_alpha).max()),
+    "alpha_mean_standard_error": se_alpha, "intercept_final_parameter_max_abs_diff": float(np.abs(np.round(alpha_d, 3) - np.round(alpha_o, 3))[keep].max()),
+    "beta_mean_rms_diff": float(np.sqrt(np.mean(d_beta ** 2))), "beta_mean_max_abs_diff": float(np.abs(d_beta).max()),
+    "beta_mean_standard_error": se_beta,
+    "effect_final_parameter_rms_diff_where_both_call": float(np.sqrt(np.mean(d_final ** 2))) if d_final.size else None,
+    "effect_final_parameter_max_abs_diff_where_both_call": float(np.abs(d_final).max()) if d_final.size else None,
+    "oracle_guard": a.oracle_guard, "posterior_mass_above_fp32_guard_from_fp64_device_run": mass,
     "workload": f"{B} datasets x {C} chains, K={K}, N={y.shape[1]}, D={D}, sample_hmc({nr},{nb}), L=10; device fp32 (kernel kind {shard.out.kernel_kind}) vs C oracle fp64, independent streams",
     "device_wall_s": t_dev, "device_kernel_ms": shard.out.kernel_ms, "oracle_wall_s": t_orc,
     "oracle_chains_in_precision_loss_mode": float(1.0 - sane.mean()), "datasets_compared": int(keep.sum()),
