@@ -119,10 +119,12 @@ struct Plan {
 };
 
 int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, int cpc_req, Plan* out) {
-    int dev = 0, max_smem = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+    int dev = 0, max_smem = 0, n_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
         cudaGetLastError();
         max_smem = 227 * 1024;  // B200; used only for planning without a device
+        n_sm = 148;
     }
     const int NK = p->N * p->K;
     const int kind_in = kind;
@@ -170,6 +172,28 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, i
         }
         out->W = W; out->cpc = cpc; out->smem = (int)smem;
         out->grid = p->B * ((p->C + cpc - 1) / cpc);
+        // A launch with more than 16 chains per SM on the case/control HMC kernel (beyond the reach of the uncapped
+        // build, kernels_cc.cu): one wide CTA per SM holding a balanced share of the chains, its warps meeting at a
+        // barrier every 16 transitions (hmc_cc.cuh: WIDE)
+        a.wide = 0;
+        const long long n_chains = (long long)p->B * p->C;
+        if (kind == sccoda::KIND_HMC_CC && cpc_req == 0 && p->C <= 28 && n_chains > (long long)n_sm * 16) {
+            const int per_sm = (int)((n_chains + n_sm - 1) / n_sm);
+            int warps = per_sm < 28 ? per_sm : 28;                            // 72 registers x 28 warps fill the register file
+            a.wide = warps;
+            a.wide_grid = per_sm <= 28 ? n_sm : (int)((n_chains + warps - 1) / warps);   // one CTA per SM, or several waves
+            while (warps > 12 && (int)sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype) > max_smem) {
+                a.wide = --warps;                                             // the staged datasets of a CTA must fit (few chains per dataset)
+                a.wide_grid = (int)((n_chains + warps - 1) / warps);
+            }
+            if ((int)sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype) <= max_smem) {
+                out->cpc = warps;
+                out->grid = a.wide_grid;
+                out->smem = (int)sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype);
+            } else {
+                a.wide = 0;
+            }
+        }
         return 0;
     }
     return fail(-9, "problem does not fit the shared memory of one CTA");

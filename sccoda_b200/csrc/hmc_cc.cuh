@@ -173,7 +173,7 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
     float* ov = sp<float>((uint32_t)pl.ov);
     float* om = sp<float>((uint32_t)pl.om);
     int* fill = sp<int>((uint32_t)pl.fill);
-    if (threadIdx.x < 64) fill[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) fill[i] = 0;
     const T* pcoef = static_cast<const T*>(a.pcoef) + (size_t)b * NP * 6;
     // rational coefficients: cf[j][lane] = (pair (0,lane), pair (1,lane)); lane K = row totals; lanes > K: zero
     for (int i = threadIdx.x; i < 6 * 32 * 2; i += blockDim.x) {
@@ -248,10 +248,9 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
         lg_sum += lg;
     }
     double* red = sp<double>((uint32_t)pl.red);
-    if (threadIdx.x < 4) red[threadIdx.x] = 0.0;
     __syncthreads();
     for (int o = 16; o > 0; o >>= 1) lg_sum += __shfl_xor_sync(0xffffffffu, lg_sum, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lg_sum;   // one slot per warp: deterministic sum below
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lg_sum;   // one slot per warp (up to 32): deterministic sum below
     // value pass, elements: (count, host constant, concentration slot u*32 + k), counts >= 6 first.  The partition
     // is done by warp 0 with ballots, in list order, so that the summation order never depends on the launch.
     float4* el = sp<float4>(t.el);
@@ -285,7 +284,9 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
     t.NT = bounds[0];
     t.NOT = bounds[1];
     t.nbig = bounds[2];
-    t.lconst = a.lconst[b] - (((red[0] + red[1]) + red[2]) + red[3]);
+    double lg_all = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) lg_all += red[w];   // rows are dealt to the threads in order: only
+    t.lconst = a.lconst[b] - lg_all;                                            // the first ceil(N / 32) warps hold a part
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -484,22 +485,64 @@ static __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off,
 // ------------------------------------------------------------------------------------------------
 // The body is shared by two entry points that differ in their register budget only:
 //   hmc_cc_kernel      72 registers, 7 CTAs of 128 threads per SM: every chain of a full sweep (>= ~2400 chains) resident
+//   hmc_cc_wide_kernel the same budget as ONE CTA of up to 28 warps per SM (see WIDE below): the sweep's launch
 //   hmc_cc_lat_kernel  no register cap: for launches that leave the device under-filled (a shard of the sweep on each
 //                      of 8 GPUs: 512 chains on 592 schedulers), where one warp per scheduler runs at the latency of its
 //                      own dependency chains and the spills / re-materialisations of the capped build are pure loss
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned sm_id() {
+    unsigned v;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(v));
+    return v;
+}
+
+// WIDE: one CTA per SM that holds a balanced share of ALL chains of the launch (a.wide = the largest share: 28 warps
+// for 4096 chains on 148 SMs; the chains are dealt out by their global index, the CTA stages every dataset its chains
+// belong to) and meets at a CTA barrier every 16 transitions.  The warp schedulers are not fair: in the narrow launch
+// (7 independent CTAs per SM) the chains of one SM finish between 30 and 59 ms of a 59 ms launch, so the SM runs its
+// last third with a fraction of its warps and little latency hiding left; chains that advance together all finish
+// together (49.8 ms for the same launch).
+template <bool WIDE>
 __device__ __forceinline__ void hmc_cc_body(const KArgs& a) {
     using T = float;
+    const unsigned long long t_start = global_timer_ns();
     const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
-    const int cpc = blockDim.x >> 5;
-    const int ctas_per_ds = (a.C + cpc - 1) / cpc;
-    const int b = blockIdx.x / ctas_per_ds;
-    const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
     const int K = a.dm.K, K1 = a.dm.K1, P = a.dm.P;
-    const CcPlan pl = plan_cc(a.dm.N, K, a.NT, a.NOT, 0);
+    CcPlan pl = plan_cc(a.dm.N, K, a.NT, a.NOT, 0);
     CcTile tile;
-    cc_stage(a, b, pl, tile);
-    if (c >= a.C) return;
-    const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
+    int b, c;
+    size_t data_bytes = pl.data_total;
+    if constexpr (WIDE) {
+        const long long n_chains = (long long)a.B * a.C;
+        const int lo = (int)(n_chains * blockIdx.x / gridDim.x), hi = (int)(n_chains * (blockIdx.x + 1) / gridDim.x);
+        const int chain_g = lo + gid;                    // global chain of this warp (>= hi: nothing to do)
+        const int b_lo = lo / a.C, b_hi = (hi - 1) / a.C;
+        b = chain_g / a.C;
+        c = chain_g - b * a.C;
+        data_bytes = (size_t)wide_datasets(a.wide, a.C) * pl.data_total;
+#pragma unroll 1
+        for (int bb = b_lo; bb <= b_hi; ++bb) {          // the whole CTA stages one dataset after the other
+            CcPlan pd = pl;
+            const size_t sh = (size_t)(bb - b_lo) * pl.data_total;
+            pd.cf += sh; pd.yv += sh; pd.ov += sh; pd.om += sh; pd.rows += sh; pd.el += sh; pd.bounds += sh; pd.red += sh; pd.fill += sh;
+            CcTile td;
+            cc_stage(a, bb, pd, td);
+            if (bb == b) tile = td;
+        }
+        if (chain_g >= hi) return;
+    } else {
+        const int cpc = blockDim.x >> 5;
+        const int ctas_per_ds = (a.C + cpc - 1) / cpc;
+        b = blockIdx.x / ctas_per_ds;
+        c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
+        cc_stage(a, b, pl, tile);
+        if (c >= a.C) return;
+    }
+    const uint32_t chain_off = (uint32_t)(data_bytes + (size_t)gid * pl.chain_total);
     const uint32_t pc_off = chain_off + (uint32_t)pl.pc;
     T* const vec = sp<T>(chain_off + (uint32_t)pl.vec);   // one flat state vector: momentum transpose, carry in / out
     const size_t chain = (size_t)b * a.C + c;
@@ -609,6 +652,9 @@ __device__ __forceinline__ void hmc_cc_body(const KArgs& a) {
             lp_cur = lp_new;
         }
         if (boot) continue;
+        if constexpr (WIDE) {
+            if ((t & 15) == 0) __syncthreads();   // the chains of the SM advance together (exited warps do not count)
+        }
         T traced_eps = eps;
         if (a.method == SCCODA_METHOD_HMC) {
             ad.simple(lar, t, a.num_adapt, log_target);
@@ -628,9 +674,16 @@ __device__ __forceinline__ void hmc_cc_body(const KArgs& a) {
     scatter(vec, thc);
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
+    // diagnostics in the spare carry slots: how long this chain ran (ns, global timer) and on which SM
+    if (a.carry != nullptr && lane == 0) {
+        double* cr = a.carry + chain * (P + SCCODA_NCARRY);
+        cr[P + 5] = (double)(global_timer_ns() - t_start);
+        cr[P + 6] = (double)sm_id();
+    }
 }
 
-__global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ KArgs a) { hmc_cc_body(a); }
+__global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ KArgs a) { hmc_cc_body<false>(a); }
+__global__ void __launch_bounds__(896, 1) hmc_cc_wide_kernel(const __grid_constant__ KArgs a) { hmc_cc_body<true>(a); }
 
 // K1cc — value and gradient at given states through cc_grad / cc_value, i.e. exactly what the sampler above evaluates
 // at every leapfrog (sccoda_logp_grad_as; target_log_prob_fn + autodiff of scCODA_model.py:756-760): theta[B,C,P] in
@@ -682,7 +735,7 @@ __global__ void __launch_bounds__(128) logp_grad_cc_kernel(const __grid_constant
     }
     if (lane == 0) a.carry[chain] = lp;
 }
-__global__ void __launch_bounds__(128, 1) hmc_cc_lat_kernel(const __grid_constant__ KArgs a) { hmc_cc_body(a); }
+__global__ void __launch_bounds__(128, 1) hmc_cc_lat_kernel(const __grid_constant__ KArgs a) { hmc_cc_body<false>(a); }
 
 // ------------------------------------------------------------------------------------------------
 // K3cc — NUTS for the same case/control shape: the iterative tree of nuts_kernel (kernels_impl.cuh; [TFP]

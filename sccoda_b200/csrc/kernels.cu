@@ -32,6 +32,7 @@ size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int d
     const size_t ts = dtype == SCCODA_F64 ? 8 : 4;
     if (kind == KIND_HMC_CC || kind == KIND_NUTS_CC) {
         const CcPlan cp = plan_cc(a.dm.N, a.dm.K, a.NT, a.NOT, kind == KIND_NUTS_CC ? 11 + 2 * (a.max_depth + 1) : 0);
+        if (kind == KIND_HMC_CC && a.wide > 0) return (size_t)wide_datasets(a.wide, a.C) * cp.data_total + (size_t)a.wide * cp.chain_total;
         return cp.data_total + (size_t)chains_per_cta * cp.chain_total;
     }
     if (kind == KIND_HMC_MG || kind == KIND_NUTS_MG) {
@@ -49,6 +50,7 @@ cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const 
     const int grid = a.B * ctas_per_ds;
     const int block = chains_per_cta * 32 * W;
     const size_t smem = smem_bytes_for(a, kind, W, chains_per_cta, dtype);
+    if (kind == KIND_HMC_CC && a.wide > 0) return launch_hmc_cc(a, a.wide_grid, a.wide * 32, smem, st);
     if (kind == KIND_HMC_CC) return launch_hmc_cc(a, grid, block, smem, st);
     if (kind == KIND_NUTS_CC) return launch_nuts_cc(a, grid, block, smem, st);
     if (kind == KIND_HMC_MG) return launch_hmc_mg(a, grid, block, smem, st);

@@ -40,6 +40,8 @@ struct KArgs {
     int method, num_results, num_burnin, num_adapt, num_leapfrog, max_depth;
     int step_begin, step_end, store_draws;
     int generic_only;  // 1: never take a specialised kernel (tests compare the specialisations with the generic path)
+    int wide;          // > 0: the wide case/control HMC launch (hmc_cc_wide_kernel): warps (= chains) of the fullest CTA
+    int wide_grid;     //      and its number of CTAs (one per SM)
     double step_size, target_accept;
     uint64_t seed;
     uint32_t chain_id0;
@@ -118,6 +120,8 @@ struct CcPlan {
     size_t pc, vec, slots, chain_total;        // per chain (relative)
     int NTC;                                   // item slots per pair: the packed items plus room for the shifted odd counts
 };
+// wide launch: datasets a CTA of `warps` consecutive chains (C per dataset) can span at most
+__host__ __device__ inline int wide_datasets(int warps, int C) { return (warps + C - 2) / C + 1; }
 // n_slots: float4-per-lane vectors of the NUTS tree (0 for HMC)
 __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT, int n_slots) {
     CcPlan p;
@@ -132,7 +136,7 @@ __host__ __device__ inline CcPlan plan_cc(int N, int K, int NT, int NOT, int n_s
     p.rows = o; o += (size_t)N * 16;                             // (row total, host-like constant, group, -)
     p.el = o; o += (size_t)N * K * 16;                           // (count, host constant, concentration slot, -)
     p.bounds = o; o += 16;                                       // int[3]: per-dataset loop bounds (items, odd counts, big elements)
-    p.red = o; o += 32;                                          // double[4]: staging reduction
+    p.red = o; o += 32 * 8;                                      // double[32]: staging reduction, one slot per warp
     p.fill = o; o += 64 * 4;                                     // int[32][2]: data counts in the item slots of every pair
     p.data_total = o;
     p.pc = 0;                                                    // float[64] concentrations, slot u*32 + column

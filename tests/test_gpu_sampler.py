@@ -609,6 +609,40 @@ def test_host_buffer_entry_point_matches_device_path():
     assert np.array_equal(summ, summ_dev)
 
 
+@pytest.mark.parametrize("B,C", [(640, 4), (900, 3), (2500, 1), (1100, 5)])
+def test_wide_launch_is_bit_identical_to_one_dataset_per_cta(B, C):
+    """Launches with more than 16 chains per SM take the wide geometry of the case/control HMC kernel (one CTA per SM
+    with a balanced share of the chains, staging every dataset they belong to, barrier every 16 transitions); chains do
+    not depend on the launch geometry: draws, statistics and the resume state are those of the classic launch."""
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    from sccoda_b200.util.data_generation import generate_sweep
+    x, y, _ = generate_sweep(B, K=20, n_per_group=10, n_total=5000, seed0=77)
+    y[3, 2, 5] = 0
+    y[B - 1, 19, 0] = 0
+    refs = np.arange(B) % 20
+    prob = DeviceProblem(pack(x, y, refs, dtype=np.float32), chains=C)
+    rs = np.random.RandomState(B)
+    init = np.zeros((B, C, prob.P), dtype=np.float32)
+    init[..., 0] = 1.0
+    init[..., 1:20] = rs.randn(B, C, 19)
+    init[..., -20:] = rs.randn(B, C, 20)
+    smp_w = prob.make_sampler(1, 40, 20, seed=5)
+    smp_c = prob.make_sampler(1, 40, 20, seed=5, chains_per_cta=min(C, 4))
+    assert prob.plan(smp_w)[1] > 12 and prob.plan(smp_c)[1] == min(C, 4)
+    ow, oc = prob.sample(init, smp_w), prob.sample(init, smp_c)
+    assert ow.kernel_kind == 3 and oc.kernel_kind == 3
+    assert torch_equal(ow.draws, oc.draws) and torch_equal(ow.stats, oc.stats)
+    P = prob.P
+    assert torch_equal(ow.carry[..., :P + 5], oc.carry[..., :P + 5])       # slots P+5, P+6 are timing diagnostics
+    assert 0.2 < ow.stat("is_accepted").mean().item() < 1.0
+
+
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)))
+
+
 def test_raw_host_entry_point_packs_and_matches_device_path():
     """sccoda_sample_raw_host (raw x / y host arrays: packer + copies + sampler + summaries inside one native call) ==
     packing in Python and sampling through the device-pointer path, bit for bit."""

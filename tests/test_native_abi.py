@@ -59,11 +59,18 @@ def _plan(prob, smp):
 
 
 def test_launch_plan_sweep_config():
-    """1024 datasets x 4 chains, K=N=20: one warp per chain, the 4 chains of a dataset share one CTA."""
+    """1024 datasets x 4 chains, K=N=20: one warp per chain; the sweep fills the device, so the planner takes the wide
+    launch — one CTA per SM with a balanced share of the 4096 chains (28 warps at most), staging the up to 8 datasets
+    they belong to.  A shard of 128 datasets (strong scaling on 8 GPUs) keeps one dataset per CTA."""
     x, y = synthetic_dataset(0)
     pk = pack(np.broadcast_to(x, (1024,) + x.shape), np.broadcast_to(y, (1024,) + y.shape), 19)
     rc, w, cpc, grid, smem = _plan(_problem(pk, 4), _sampler())
+    assert rc == 0 and w == 1 and cpc == 28 and grid == 148 and 100 * 1024 < smem < 227 * 1024
+    rc, w, cpc, grid, smem = _plan(_problem(pk, 4), _sampler(chains_per_cta=4))          # an explicit geometry is kept
     assert rc == 0 and w == 1 and cpc == 4 and grid == 1024 and 0 < smem < 48 * 1024
+    pk = pack(np.broadcast_to(x, (128,) + x.shape), np.broadcast_to(y, (128,) + y.shape), 19)
+    rc, w, cpc, grid, smem = _plan(_problem(pk, 4), _sampler())
+    assert rc == 0 and w == 1 and cpc == 4 and grid == 128 and 0 < smem < 48 * 1024
 
 
 def test_launch_plan_scales_warps_for_few_chains_and_big_models():
