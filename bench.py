@@ -399,14 +399,15 @@ def run_ours(a):
     draw_bytes = float(B) * C * a.num_results * (P + nat.NSTAT) * 4
     traffic = traffic_from_profile(out.kernel_kind, a, world)
     plan = prob.plan(sh.smp)
-    lat = out.kernel_kind == 3 and plan[2] * plan[1] * plan[0] <= 148 * 16
+    wide = out.kernel_kind == 3 and plan[1] > C                 # one CTA per SM with a share of all chains (hmc_cc.cuh)
+    lat = out.kernel_kind == 3 and not wide and plan[2] * plan[1] * plan[0] <= 148 * 16
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None,
                 "traffic": traffic["bytes"] if traffic else None, "traffic_detail": traffic,
                 "peak_source": "FFMA micro-kernel measured in this run on this device (sccoda_measure_peaks); "
                                "MEASURED_PEAKS.json has no fp32 entry",
                 "mufu_peak_tops": mufu_peak,
-                "kernel": {1: "hmc_kernel<float,W,grouped>", 3: "hmc_cc_lat_kernel" if lat else "hmc_cc_kernel",
+                "kernel": {1: "hmc_kernel<float,W,grouped>", 3: "hmc_cc_wide_kernel" if wide else ("hmc_cc_lat_kernel" if lat else "hmc_cc_kernel"),
                            5: "hmc_mg_kernel<D>"}.get(out.kernel_kind, "hmc_kernel"), "kernel_ms": k_ms,
                 "summary_kernel_ms": s_ms, "algorithmic_flop_per_launch": flops_launch,
                 "flop_model": "per grad-eval 64NK+48N+4NKD, per value 28(2NK+2N) (SURVEY 8d)",
@@ -469,8 +470,13 @@ def run_ours(a):
         shw = Shard(rank * a.datasets, (rank + 1) * a.datasets, a.datasets * world)
         outw, _, ms_w, ge_w, _ = shw.timed(1, a.weak_extra_steps)
         kw, sw, gw = shw.phases_ms()
+        allw = comm.gather_blocks(torch.tensor([[kw, sw, gw]], dtype=torch.float64, device=dev), world).cpu().numpy()
         weak = {"value": ge_w / (ms_w * 1e-3), "unit": UNIT, "ms_per_step": ms_w, "datasets_per_gpu": a.datasets,
-                "steps": a.weak_extra_steps, "kernel_ms_rank0": kw, "summary_ms_rank0": sw, "gather_ms_rank0": gw}
+                "steps": a.weak_extra_steps, "kernel_ms_per_rank": [round(float(v), 3) for v in allw[:, 0]],
+                "summary_ms_per_rank": [round(float(v), 3) for v in allw[:, 1]],
+                "gather_ms_per_rank": [round(float(v), 3) for v in allw[:, 2]],
+                "note": "each rank samples its own 1024 datasets (global ids rank*1024 ...): the kernel times differ with "
+                        "the data, and the gather waits for the slowest rank"}
         del outw
         shw.draws = shw.stats = None
         torch.cuda.empty_cache()
