@@ -564,6 +564,61 @@ def test_fp32_statistical_parity_nuts(variant):
     assert np.all(np.abs(am.mean(0) - ar.mean(0)) < 5 * se + 0.05), (am.mean(0), ar.mean(0))
 
 
+def _config3_data():
+    """BASELINE config 3: N = 200 samples, K = 50 cell types, D = 4 binary covariates (SURVEY §8d recipe)."""
+    rs = np.random.RandomState(1234)
+    N, K, D = 200, 50, 4
+    x = rs.randint(0, 2, size=(N, D)).astype(float)
+    bt = rs.uniform(-3, 3, size=K)
+    wt = np.zeros((D, K))
+    for dd in range(D):
+        wt[dd, rs.choice(K - 1, 3, replace=False)] = rs.choice([0.3, 0.5, 1.0], 3)
+    logits = x @ wt + bt + np.sqrt(0.05) * rs.randn(N, K)
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    y = np.stack([rs.multinomial(5000, p[n]) for n in range(N)]).astype(float)
+    return x, y
+
+
+def test_config3_shape_nuts_fp64_trajectory_and_fp32_statistics():
+    """BASELINE config 3 (N = 200, K = 50, D = 4, sample_nuts, 16 warps per chain): the fp64 build walks the oracle's
+    first NUTS transitions, and the fp32 production build agrees with the oracle statistically (leapfrogs per draw, accept
+    statistic, step size, intercept means) on short chains with dual averaging (the long version of the comparison is
+    tools/nuts_cfg3_parity.py -> profiles/r2_nuts_cfg3_parity.json; the oracle needs minutes for it)."""
+    from sccoda_b200.engine import DeviceProblem
+    x, y = _config3_data()
+    K, D, C = 50, 4, 4
+    init = _init(np.random.RandomState(4), D, K, C)
+    init[:, -K:] = np.log(y.mean(0) / y.mean(0).sum() * 50.0) + 0.1 * init[:, -K:]    # intercepts near the data: no long transient
+    # fp64: identical Philox streams, trees of up to 2^6 leaves
+    d_ref, s_ref = _oracle_run(x, y, K - 1, init[:2], 2, 4, 0, num_adapt=4, seed=5, chain_id0=1, max_tree_depth=6)
+    prob64 = DeviceProblem.from_arrays(x, y, K - 1, chains=2, dtype=np.float64)
+    out = prob64.sample(init[None, :2], prob64.make_sampler(2, 4, 0, num_adapt=4, seed=5, chain_id0=1, max_tree_depth=6))
+    assert out.kernel_kind == 2 and out.warps_per_chain == 16
+    assert np.array_equal(out.stat("leapfrogs_taken").cpu().numpy(), s_ref["leapfrogs_taken"])
+    assert np.abs(out.draws.cpu().numpy() - d_ref).max() < 1e-6
+    # fp32: the config's sampler (depth 10, dual averaging), independent streams
+    nr, nb = 20, 60
+    d_ref, s_ref = _oracle_run(x, y, K - 1, init, 2, nr, nb, seed=41, chain_id0=0)
+    prob = DeviceProblem.from_arrays(x, y, K - 1, chains=C, dtype=np.float32)
+    out = prob.sample(init[None], prob.make_sampler(2, nr, nb, seed=42))
+    assert out.kernel_kind == 2 and out.warps_per_chain == 16
+    d = out.draws.double().cpu().numpy()
+    assert np.isfinite(d).all()
+    lf, lf_r = out.stat("leapfrogs_taken").double().cpu().numpy()[0].mean(), s_ref["leapfrogs_taken"][0].mean()
+    assert abs(np.log(lf / lf_r)) < 0.35, (lf, lf_r)
+    a = np.exp(np.minimum(out.stat("log_accept_ratio").double().cpu().numpy()[0], 0)).mean()
+    a_r = np.exp(np.minimum(s_ref["log_accept_ratio"][0], 0)).mean()
+    assert abs(a - a_r) < 0.08, (a, a_r)
+    eps, eps_r = out.stat("step_size").double().cpu().numpy()[0, :, -1].mean(), s_ref["step_size"][0, :, -1].mean()
+    assert abs(np.log(eps / eps_r)) < 0.35, (eps, eps_r)
+    am, ar = d[0, :, :, -K:].mean(1), d_ref[0, :, :, -K:].mean(1)                  # [C,K] intercept means per chain
+    se = np.hypot(am.std(0, ddof=1), ar.std(0, ddof=1)) / np.sqrt(C)
+    assert np.all(np.abs(am.mean(0) - ar.mean(0)) < 5 * se + 0.05), np.abs(am.mean(0) - ar.mean(0)).max()
+    lp, lp_r = out.stat("target_log_prob").double().cpu().numpy()[0], s_ref["target_log_prob"][0]
+    assert abs(lp.mean() - lp_r.mean()) < 5 * np.hypot(lp.std(), lp_r.std()) / np.sqrt(C) + 25.0, (lp.mean(), lp_r.mean())
+
+
 def test_summary_kernel_matches_numpy():
     """K4 vs the numpy restatement of get_y_hat / complete_beta_df arithmetic on the same draws."""
     from oracle import np_oracle as o
