@@ -177,11 +177,20 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, i
         // barrier every 16 transitions (hmc_cc.cuh: WIDE)
         a.wide = 0;
         const long long n_chains = (long long)p->B * p->C;
-        if (kind == sccoda::KIND_HMC_CC && cpc_req == 0 && p->C <= 28 && n_chains > (long long)n_sm * 16) {
+        // warps one SM holds of this kernel (its register budget): 28 for the case/control kernel, 4 x the resident CTAs
+        // of 128 threads the multi-group kernel is compiled for
+        const int wmax = kind == sccoda::KIND_HMC_CC ? 28 : (kind == sccoda::KIND_HMC_MG ? 4 * sccoda::mg_hmc_ctas(p->D, p->K <= 31 ? 1 : 2) : 0);
+        const long long wide_from = kind == sccoda::KIND_HMC_CC ? 16 : (wmax * 2) / 3;   // chains per SM from which the wide launch pays
+        // ... and only when the CTAs of the launch fill whole waves: one wave, or several with the last one >= 90 % full
+        // (a CTA holds the SM alone; a sparse last wave costs more than the fair scheduling gains)
+        const long long per_wave = (long long)n_sm * (wmax > 0 ? wmax : 1);
+        const long long last_wave = n_chains % per_wave;
+        const bool whole_waves = n_chains <= per_wave || last_wave == 0 || last_wave * 10 >= per_wave * 9;
+        if (wmax > 0 && cpc_req == 0 && p->C <= wmax && n_chains > (long long)n_sm * wide_from && whole_waves) {
             const int per_sm = (int)((n_chains + n_sm - 1) / n_sm);
-            int warps = per_sm < 28 ? per_sm : 28;                            // 72 registers x 28 warps fill the register file
+            int warps = per_sm < wmax ? per_sm : wmax;                        // 72 registers x 28 warps fill the register file
             a.wide = warps;
-            a.wide_grid = per_sm <= 28 ? n_sm : (int)((n_chains + warps - 1) / warps);   // one CTA per SM, or several waves
+            a.wide_grid = per_sm <= wmax ? n_sm : (int)((n_chains + warps - 1) / warps);   // one CTA per SM, or several waves
             while (warps > 12 && (int)sccoda::smem_bytes_for(a, kind, W, cpc, p->dtype) > max_smem) {
                 a.wide = --warps;                                             // the staged datasets of a CTA must fit (few chains per dataset)
                 a.wide_grid = (int)((n_chains + warps - 1) / warps);

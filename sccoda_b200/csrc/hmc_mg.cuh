@@ -156,10 +156,9 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
         lg_sum += lg;
     }
     double* red = sp<double>((uint32_t)pl.red);
-    if (threadIdx.x < 4) red[threadIdx.x] = 0.0;
     __syncthreads();
     for (int o = 16; o > 0; o >>= 1) lg_sum += __shfl_xor_sync(0xffffffffu, lg_sum, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lg_sum;   // one slot per warp: deterministic sum below
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lg_sum;   // one slot per warp (up to 32): deterministic sum below
     float4* el = sp<float4>((uint32_t)pl.el);
     const T* ey = static_cast<const T*>(a.ey) + (size_t)b * NK;
     const T* eycst = static_cast<const T*>(a.eycst) + (size_t)b * NK;
@@ -190,7 +189,9 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
     }
     __syncthreads();
     t.nbig = bounds[2 * NQ];
-    t.lconst = a.lconst[b] - (((red[0] + red[1]) + red[2]) + red[3]);
+    double lg_all = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) lg_all += red[w];
+    t.lconst = a.lconst[b] - lg_all;
 }
 
 // The parameters a lane owns: per column slot s (cell type 32 s + lane) alpha and, per covariate, b_offset and
@@ -527,29 +528,52 @@ __device__ __forceinline__ float mg_dot(const MgVec<D, NS>& x, const MgVec<D, NS
     return lane == 0 ? v + sv : v;
 }
 
-// resident CTAs of 128 threads per SM the kernels are compiled for (register caps)
-constexpr int mg_hmc_ctas(int D, int NS) { return NS == 1 ? (D == 1 ? 6 : (D == 2 ? 5 : (D == 3 ? 4 : 3))) : (D == 1 ? 4 : (D == 2 ? 3 : 2)); }
-constexpr int mg_nuts_ctas(int D, int NS) { return NS == 1 ? (D == 1 ? 4 : (D <= 2 ? 3 : 2)) : (D == 1 ? 3 : (D == 2 ? 2 : 1)); }
+// (mg_hmc_ctas / mg_nuts_ctas, the resident CTAs of 128 threads per SM the kernels are compiled for, live in kernels.h)
 
 // ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
-template <int D, int NS>
-__global__ void __launch_bounds__(128, mg_hmc_ctas(D, NS)) hmc_mg_kernel(const __grid_constant__ KArgs a) {
+// WIDE: the launch geometry of hmc_cc_wide_kernel (hmc_cc.cuh) — one CTA per SM with a balanced share of all chains of the
+// launch, meeting at a barrier every 16 transitions so that the unfair warp schedulers cannot drain the SM early.
+template <int D, int NS, bool WIDE>
+__device__ __forceinline__ void hmc_mg_body(const KArgs& a) {
     using T = float;
     using V = MgVec<D, NS>;
     const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
-    const int cpc = blockDim.x >> 5;
-    const int ctas_per_ds = (a.C + cpc - 1) / cpc;
-    const int b = blockIdx.x / ctas_per_ds;
-    const int c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
     const int K = a.dm.K, P = a.dm.P;
     const int UPmax = (a.Umax + 1) >> 1;
     const MgPlan pl = plan_mg(a.dm.N, K, D, UPmax, NS, a.NT, a.NOT, 0);
     MgTile tile;
-    mg_stage(a, b, pl, UPmax, NS, tile);
-    if (c >= a.C) return;
-    const uint32_t chain_off = (uint32_t)(pl.data_total + (size_t)gid * pl.chain_total);
+    int b, c;
+    size_t data_bytes = pl.data_total;
+    if constexpr (WIDE) {
+        const long long n_chains = (long long)a.B * a.C;
+        const int lo = (int)(n_chains * blockIdx.x / gridDim.x), hi = (int)(n_chains * (blockIdx.x + 1) / gridDim.x);
+        const int chain_g = lo + gid;
+        const int b_lo = lo / a.C, b_hi = (hi - 1) / a.C;
+        b = chain_g / a.C;
+        c = chain_g - b * a.C;
+        data_bytes = (size_t)wide_datasets(a.wide, a.C) * pl.data_total;
+#pragma unroll 1
+        for (int bb = b_lo; bb <= b_hi; ++bb) {
+            MgPlan pd = pl;
+            const size_t sh = (size_t)(bb - b_lo) * pl.data_total;
+            pd.cf += sh; pd.yv += sh; pd.ov += sh; pd.om += sh; pd.rows += sh; pd.el += sh; pd.xg += sh; pd.cnt += sh;
+            pd.bounds += sh; pd.red += sh; pd.fill += sh;
+            MgTile td;
+            mg_stage(a, bb, pd, UPmax, NS, td);
+            if (bb == b) tile = td;
+        }
+        if (chain_g >= hi) return;
+    } else {
+        const int cpc = blockDim.x >> 5;
+        const int ctas_per_ds = (a.C + cpc - 1) / cpc;
+        b = blockIdx.x / ctas_per_ds;
+        c = (blockIdx.x - b * ctas_per_ds) * cpc + gid;
+        mg_stage(a, b, pl, UPmax, NS, tile);
+        if (c >= a.C) return;
+    }
+    const uint32_t chain_off = (uint32_t)(data_bytes + (size_t)gid * pl.chain_total);
     const uint32_t pc_off = pin_u32(chain_off + (uint32_t)pl.pc);
     T* const vec = sp<T>(pin_u32(chain_off + (uint32_t)pl.vec));   // one flat state vector: momentum transpose, carry in / out
     const size_t chain = (size_t)b * a.C + c;
@@ -635,6 +659,9 @@ __global__ void __launch_bounds__(128, mg_hmc_ctas(D, NS)) hmc_mg_kernel(const _
             lp_cur = lp_new;
         }
         if (boot) continue;
+        if constexpr (WIDE) {
+            if ((t & 15) == 0) __syncthreads();   // the chains of the SM advance together (exited warps do not count)
+        }
         T traced_eps = eps;
         if (a.method == SCCODA_METHOD_HMC) {
             ad.simple(lar, t, a.num_adapt, log_target);
@@ -654,6 +681,15 @@ __global__ void __launch_bounds__(128, mg_hmc_ctas(D, NS)) hmc_mg_kernel(const _
     mp.scatter(vec, thc, lane);
     __syncwarp();
     store_chain_state<T>(a, chain, vec, ad, lp_cur, lane, 32);
+}
+
+template <int D, int NS>
+__global__ void __launch_bounds__(128, mg_hmc_ctas(D, NS)) hmc_mg_kernel(const __grid_constant__ KArgs a) {
+    hmc_mg_body<D, NS, false>(a);
+}
+template <int D, int NS>
+__global__ void __launch_bounds__(128 * mg_hmc_ctas(D, NS), 1) hmc_mg_wide_kernel(const __grid_constant__ KArgs a) {
+    hmc_mg_body<D, NS, true>(a);
 }
 
 // K1mg — value and gradient at given states through mg_grad / mg_value (sccoda_logp_grad_as): theta[B,C,P] in a.init,

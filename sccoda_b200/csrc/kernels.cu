@@ -38,6 +38,7 @@ size_t smem_bytes_for(const KArgs& a, int kind, int W, int chains_per_cta, int d
     if (kind == KIND_HMC_MG || kind == KIND_NUTS_MG) {
         const MgPlan mp = plan_mg(a.dm.N, a.dm.K, a.dm.D, (a.Umax + 1) / 2, a.dm.K <= 31 ? 1 : 2, a.NT, a.NOT,
                                   kind == KIND_NUTS_MG ? 11 + 2 * (a.max_depth + 1) : 0);
+        if (kind == KIND_HMC_MG && a.wide > 0) return (size_t)wide_datasets(a.wide, a.C) * mp.data_total + (size_t)a.wide * mp.chain_total;
         return mp.data_total + (size_t)chains_per_cta * mp.chain_total;
     }
     const SmemPlan pl = plan_smem(a.dm.N, a.dm.K, a.dm.D, a.Umax, a.el_smem ? a.el_count : 0, a.grouped ? a.NImax : 0, a.NF,
@@ -53,6 +54,7 @@ cudaError_t launch_kernel(int kind, int dtype, int W, int chains_per_cta, const 
     if (kind == KIND_HMC_CC && a.wide > 0) return launch_hmc_cc(a, a.wide_grid, a.wide * 32, smem, st);
     if (kind == KIND_HMC_CC) return launch_hmc_cc(a, grid, block, smem, st);
     if (kind == KIND_NUTS_CC) return launch_nuts_cc(a, grid, block, smem, st);
+    if (kind == KIND_HMC_MG && a.wide > 0) return launch_hmc_mg(a, a.wide_grid, a.wide * 32, smem, st);
     if (kind == KIND_HMC_MG) return launch_hmc_mg(a, grid, block, smem, st);
     if (kind == KIND_NUTS_MG) return launch_nuts_mg(a, grid, block, smem, st);
     if (a.grouped) {

@@ -40,7 +40,7 @@ struct KArgs {
     int method, num_results, num_burnin, num_adapt, num_leapfrog, max_depth;
     int step_begin, step_end, store_draws;
     int generic_only;  // 1: never take a specialised kernel (tests compare the specialisations with the generic path)
-    int wide;          // > 0: the wide case/control HMC launch (hmc_cc_wide_kernel): warps (= chains) of the fullest CTA
+    int wide;          // > 0: the wide HMC launch (hmc_cc_wide_kernel, hmc_mg_wide_kernel): warps (= chains) of the fullest CTA
     int wide_grid;     //      and its number of CTAs (one per SM)
     double step_size, target_accept;
     uint64_t seed;
@@ -155,6 +155,10 @@ struct MgPlan {
     int NTC;                                                          // item slots per pair incl. room for the shifted odd counts (CcPlan)
 };
 constexpr int kMgMaxGroups = 32, kMgMaxD = 4, kMgMaxK = 62, kMgMaxD2 = 3 /* largest D with two cell types per lane */;
+// resident CTAs of 128 threads per SM the multi-group kernels are compiled for (register caps); the wide HMC launch is
+// ONE CTA of as many warps (4 x mg_hmc_ctas)
+__host__ __device__ constexpr int mg_hmc_ctas(int D, int NS) { return NS == 1 ? (D == 1 ? 6 : (D == 2 ? 5 : (D == 3 ? 4 : 3))) : (D == 1 ? 4 : (D == 2 ? 3 : 2)); }
+__host__ __device__ constexpr int mg_nuts_ctas(int D, int NS) { return NS == 1 ? (D == 1 ? 4 : (D <= 2 ? 3 : 2)) : (D == 1 ? 3 : (D == 2 ? 2 : 1)); }
 // float4 per lane of one stored state vector: NS (alpha + D b_offset + D ind_raw) + D sigma
 __host__ __device__ constexpr int mg_vec_quads(int D, int NS) { return (NS * (1 + 2 * D) + D + 3) / 4; }
 // n_slots: stored vectors of the NUTS tree (0 for HMC)
@@ -172,7 +176,7 @@ __host__ __device__ inline MgPlan plan_mg(int N, int K, int D, int UP, int NS, i
     p.xg = o; o += rnd16((size_t)UP * D * 8);                    // f32x2[UP][D] covariate values of the groups
     p.cnt = o; o += rnd16((size_t)UP * 2 * 4);                   // float[2 UP] rows per group
     p.bounds = o; o += rnd16((size_t)(2 * Q + 1) * 4);           // int: items / odd counts per (group pair, slot), big elements
-    p.red = o; o += 32;                                          // double[4]: staging reduction
+    p.red = o; o += 32 * 8;                                      // double[32]: staging reduction, one slot per warp
     p.fill = o; o += Q * 64 * 4;                                 // int[UP][NS][32][2]: data counts in the item slots of every pair
     p.data_total = o;
     const size_t P = (size_t)D + 2 * (size_t)D * (K - 1) + K;

@@ -5,6 +5,12 @@
 namespace sccoda {
 template <int D, int NS>
 static cudaError_t launch_hmc_mg_d(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    if (a.wide > 0) {
+        cudaError_t e = cudaFuncSetAttribute(hmc_mg_wide_kernel<D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hmc_mg_wide_kernel<D, NS><<<grid, block, smem, st>>>(a);
+        return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(hmc_mg_kernel<D, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     hmc_mg_kernel<D, NS><<<grid, block, smem, st>>>(a);

@@ -693,6 +693,35 @@ def test_wide_launch_is_bit_identical_to_one_dataset_per_cta(B, C):
     assert 0.2 < ow.stat("is_accepted").mean().item() < 1.0
 
 
+@pytest.mark.parametrize("conditions,K,B,C", [(3, 20, 520, 4), (4, 12, 700, 3), (3, 40, 460, 4)])
+def test_wide_launch_of_the_multi_group_kernel_is_bit_identical(conditions, K, B, C):
+    """The same geometry for the multi-group HMC kernels (one CTA per SM of 4 x the resident CTAs' warps): one-hot coded
+    conditions, K <= 31 and two cell types per lane; bit-identical to one dataset per CTA."""
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    from sccoda_b200.util.data_generation import generate_sweep
+    N = 5 * conditions
+    _, y, _ = generate_sweep(B, K=K, n_per_group=(N + 1) // 2, n_total=5000, seed0=99)
+    y = y[:, :N]
+    y[1, 2, 3] = 0
+    lv = np.arange(N) % conditions
+    x = np.broadcast_to((lv[:, None] == np.arange(1, conditions)[None, :]).astype(float), (B, N, conditions - 1)).copy()
+    D = conditions - 1
+    prob = DeviceProblem(pack(x, y, K - 1, dtype=np.float32), chains=C)
+    rs = np.random.RandomState(B)
+    init = np.zeros((B, C, prob.P), dtype=np.float32)
+    init[..., :D] = 1.0
+    init[..., D:D + D * (K - 1)] = rs.randn(B, C, D * (K - 1))
+    init[..., -K:] = rs.randn(B, C, K)
+    smp_w = prob.make_sampler(0, 30, 20, seed=6)
+    smp_c = prob.make_sampler(0, 30, 20, seed=6, chains_per_cta=min(C, 4))
+    assert prob.plan(smp_w)[1] > 4 and prob.plan(smp_c)[1] == min(C, 4)
+    ow, oc = prob.sample(init, smp_w), prob.sample(init, smp_c)
+    assert ow.kernel_kind == 5 and oc.kernel_kind == 5
+    assert torch_equal(ow.draws, oc.draws) and torch_equal(ow.stats, oc.stats)
+    assert torch_equal(ow.carry[..., :prob.P + 5], oc.carry[..., :prob.P + 5])
+
+
 def torch_equal(a, b):
     import torch
     return bool(torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)))
