@@ -267,6 +267,10 @@ def run_sweep(x: np.ndarray, y: np.ndarray, ref, cfg: SweepConfig, comm: Optiona
     on every rank, this rank's SweepShard)."""
     comm = comm or Comm()
     B = x.shape[0]
+    if B < comm.world:
+        # a rank without a dataset has nothing to pack or sample and no shapes to contribute to the gather
+        raise ValueError(f"run_sweep needs at least one dataset per rank: {B} dataset(s) on {comm.world} ranks; "
+                         f"launch at most {max(B, 1)} rank(s) for this sweep")
     keep = {}
 
     def compute(lo, hi):

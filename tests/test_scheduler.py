@@ -66,6 +66,15 @@ def test_gather_over_gloo(tmp_path, world, n_items):
         assert got["mx"] == world and got["sm"] == world * (world + 1) / 2
 
 
+def test_run_sweep_refuses_more_ranks_than_datasets():
+    """A rank without a dataset would have nothing to pack and no shapes for the gather: a clear error on every rank,
+    before anything touches the device."""
+    x, y = np.zeros((2, 6, 1)), np.ones((2, 6, 4))
+    for rank in range(4):
+        with pytest.raises(ValueError, match="at least one dataset per rank"):
+            sch.run_sweep(x, y, 3, sch.SweepConfig(), comm=sch.Comm(rank=rank, world=4))
+
+
 def test_credible_effect_calls_follow_the_reference_threshold_rule():
     inc = np.array([[1.0, 0.4, 0.0, 0.97], [0.2, 0.1, 0.0, 0.0]])
     nz = np.array([[0.5, 0.2, 0.0, -0.3], [0.1, 0.1, 0.0, 0.0]])

@@ -30,3 +30,17 @@ for v in np.unique(odd):
     print("datasets with max odd group", v, ":", (odd == v).sum(), "mean chain ms %.2f" % ns[odd == v].mean())
 h, e = np.histogram(ns, bins=12)
 print("histogram", list(zip(np.round(e[:-1], 1), h)))
+# the slowest datasets: what sets them apart?
+dr = out.draws.float()
+amax = dr[..., -20:].amax(dim=(1, 2, 3)).cpu().numpy()                      # largest alpha_k seen by any chain of the dataset
+sig = dr[..., 0]
+beta_max = (sig.unsqueeze(-1) * dr[..., 1:20]).abs().amax(dim=(1, 2, 3)).cpu().numpy()
+ds_ms = ns.max(axis=1)
+order = np.argsort(-ds_ms)[:12]
+zeros = (y == 0).sum(axis=(1, 2))
+small = ((y > 0) & (y < 6)).sum(axis=(1, 2))
+for b in order:
+    print(f"dataset {b}: {ds_ms[b]:.2f} ms  max alpha {amax[b]:.2f} (c ~ {np.exp(amax[b]):.0f})  |sigma b|max {beta_max[b]:.2f}  zeros {zeros[b]} small {small[b]} odd-max {odd[b]}")
+print("fast ones:")
+for b in np.argsort(ds_ms)[:5]:
+    print(f"dataset {b}: {ds_ms[b]:.2f} ms  max alpha {amax[b]:.2f} (c ~ {np.exp(amax[b]):.0f})  zeros {zeros[b]} small {small[b]} odd-max {odd[b]}")
