@@ -22,10 +22,13 @@ ap.add_argument("--W", type=int, default=0)
 ap.add_argument("--grouped", type=int, default=-1)
 ap.add_argument("--depth", type=int, default=10)
 ap.add_argument("--method", type=int, default=2)
+ap.add_argument("--D", type=int, default=4)
+ap.add_argument("--N", type=int, default=200)
+ap.add_argument("--K", type=int, default=50)
 a = ap.parse_args()
 
 rs = np.random.RandomState(1234)
-N, K, D = 200, 50, 4
+N, K, D = a.N, a.K, a.D
 x = rs.randint(0, 2, size=(N, D)).astype(float)
 bt = rs.uniform(-3, 3, size=K)
 wt = np.zeros((D, K))
