@@ -664,7 +664,7 @@ def test_host_buffer_entry_point_matches_device_path():
     assert np.array_equal(summ, summ_dev)
 
 
-@pytest.mark.parametrize("B,C", [(640, 4), (900, 3), (2500, 1), (1100, 5)])
+@pytest.mark.parametrize("B,C", [(640, 4), (900, 3), (2500, 1), (828, 5), (2072, 4)])   # the last one: two full waves
 def test_wide_launch_is_bit_identical_to_one_dataset_per_cta(B, C):
     """Launches with more than 16 chains per SM take the wide geometry of the case/control HMC kernel (one CTA per SM
     with a balanced share of the chains, staging every dataset they belong to, barrier every 16 transitions); chains do
@@ -691,9 +691,17 @@ def test_wide_launch_is_bit_identical_to_one_dataset_per_cta(B, C):
     P = prob.P
     assert torch_equal(ow.carry[..., :P + 5], oc.carry[..., :P + 5])       # slots P+5, P+6 are timing diagnostics
     assert 0.2 < ow.stat("is_accepted").mean().item() < 1.0
+    if C == 4:
+        # chunked launches resume through the carry (each chunk is its own wide launch, barriers restart at the chunk's
+        # first transition) and the SimpleModel variant (frozen sigma_d / ind_raw) takes the same geometry
+        och = prob.sample(init, prob.make_sampler(1, 40, 20, seed=5), chunk=23)
+        assert och.launches == 3 and torch_equal(och.draws, oc.draws) and torch_equal(och.stats, oc.stats)
+        fw = prob.sample(init, prob.make_sampler(0, 30, 10, seed=9, freeze_spike_slab=True))
+        fc = prob.sample(init, prob.make_sampler(0, 30, 10, seed=9, freeze_spike_slab=True, chains_per_cta=4))
+        assert torch_equal(fw.draws, fc.draws) and bool((fw.draws[..., 0] == 1.0).all())
 
 
-@pytest.mark.parametrize("conditions,K,B,C", [(3, 20, 520, 4), (4, 12, 700, 3), (3, 40, 460, 4)])
+@pytest.mark.parametrize("conditions,K,B,C", [(3, 20, 520, 4), (4, 12, 700, 3), (3, 40, 440, 4)])
 def test_wide_launch_of_the_multi_group_kernel_is_bit_identical(conditions, K, B, C):
     """The same geometry for the multi-group HMC kernels (one CTA per SM of 4 x the resident CTAs' warps): one-hot coded
     conditions, K <= 31 and two cell types per lane; bit-identical to one dataset per CTA."""
