@@ -97,7 +97,10 @@ extern "C" {
 #define SCCODA_ST_ENERGY 6
 #define SCCODA_ST_REACH_MAX_DEPTH 7
 
-/* carry[B,C,P+SCCODA_NCARRY] f64: chain state for chunked launches (resume points) */
+/* carry[B,C,P+SCCODA_NCARRY] f64: chain state for chunked launches (resume points): the P parameters, then
+ * [P+0] step size, [P+1] dual-averaging error sum, [P+2] log averaged step, [P+3] adaptation step count,
+ * [P+4] log-density of the state; [P+5], [P+6] are diagnostics the case/control HMC kernel fills (run time of the
+ * chain inside the launch in ns, SM it ran on; not read on resume), [P+7] spare */
 #define SCCODA_NCARRY 8
 
 /* summary[B,C,SCCODA_NSUM_PARAM*P + SCCODA_NSUM_BETA*D*K + SCCODA_NSUM_SCALAR] f64 — see sccoda_summarize */
@@ -206,7 +209,11 @@ int sccoda_summarize(const sccoda_problem* prob, int32_t num_results, int32_t sk
 int sccoda_predict(const sccoda_problem* prob, const int32_t* row_order, int32_t num_results, int32_t draw_begin,
                    int32_t draw_end, const void* draws, void* concentration, void* prediction, void* stream);
 
-/* Bytes of dynamic shared memory and threads per CTA the sampler would use (for planning / tests). */
+/* Launch geometry the sampler would use (for planning / tests): warps per chain, chains per CTA, CTAs, bytes of dynamic
+ * shared memory per CTA.  One warp per chain on the lane-per-cell-type kernels; HMC launches with more than ~16 chains
+ * per SM that fill whole waves take the wide geometry — one CTA per SM holding a balanced share of ALL chains (up to 28
+ * for the case/control kernel) and every dataset they belong to, its warps meeting at a barrier every 16 transitions;
+ * an explicit sccoda_sampler::chains_per_cta keeps one dataset per CTA.  Chains do not depend on the geometry. */
 int sccoda_launch_plan(const sccoda_problem* prob, const sccoda_sampler* smp, int32_t* warps_per_chain,
                        int32_t* chains_per_cta, int32_t* grid, int32_t* smem_bytes);
 
