@@ -83,11 +83,8 @@ __device__ __forceinline__ f32x2 psi_any2(f32x2 x) {
 
 // lgamma(c + y) - lgamma(y) for two counts y >= 6 at once (lgamma_shift_big of special.cuh on pairs):
 //   (y - 1/2) log1p(c/y) + c (ln(c+y) - 1) + r(c+y) - r(y),   ycst = r(y) and yinv = 1/y from staging
-__device__ __forceinline__ f32x2 lgamma_shift_big2(f32x2 c, f32x2 y, f32x2 ycst, f32x2 yinv) {
-    const f32x2 z = add2(c, y);
-    const f32x2 w = rcp2(z);
-    const f32x2 t = mul2(c, yinv);
-    // log1p(t), t >= 0: ln(1+t) by MUFU for t >= 1/2, 2 atanh(t/(2+t)) as an odd series below (log1p_pos)
+// log1p(t), t >= 0, on pairs: ln(1+t) by MUFU for t >= 1/2, 2 atanh(t/(2+t)) as an odd series below (log1p_pos)
+__device__ __forceinline__ f32x2 log1p_pos2(f32x2 t) {
     const f32x2 sq = mul2(t, rcp2(add2(t, dup2(2.0f))));
     const f32x2 s2 = mul2(sq, sq);
     f32x2 ser = fma2(s2, dup2(2.0f / 9.0f), dup2(2.0f / 7.0f));
@@ -95,7 +92,32 @@ __device__ __forceinline__ f32x2 lgamma_shift_big2(f32x2 c, f32x2 y, f32x2 ycst,
     ser = fma2(s2, ser, dup2(2.0f / 3.0f));
     ser = mul2(sq, fma2(s2, ser, dup2(2.0f)));
     const f32x2 big = mul2(lg2_2(add2(t, dup2(1.0f))), dup2(SCCODA_LN2F));
-    const f32x2 l1p = pk2(lo2(t) >= 0.5f ? lo2(big) : lo2(ser), hi2(t) >= 0.5f ? hi2(big) : hi2(ser));
+    return pk2(lo2(t) >= 0.5f ? lo2(big) : lo2(ser), hi2(t) >= 0.5f ? hi2(big) : hi2(ser));
+}
+__device__ __forceinline__ f32x2 stirling_rem2(f32x2 w) {
+    const f32x2 w2 = mul2(w, w);
+    return mul2(w, fma2(w2, fma2(w2, dup2(1.0f / 1260.0f), dup2(-1.0f / 360.0f)), dup2(1.0f / 12.0f)));
+}
+// Two counts y >= 6 whose pairs may or may not have a concentration >= c_joint: per element either
+// lgamma_shift_big (as above) or the joint form lgamma_joint of special.cuh,
+//   (c-1/2) log1p(y/c) + (y-1/2) log1p(c/y) + ln(z)/2 - ln(2 pi)/2 + r(z) - r(c) - r(y),
+// sharing z, 1/z, ln z, log1p(c/y) and r(z) between the two forms (the value pass of a state with a large concentration)
+__device__ __forceinline__ f32x2 lgamma_mixed_big2(f32x2 c, f32x2 y, f32x2 ycst, f32x2 yinv, float c_joint) {
+    const f32x2 z = add2(c, y);
+    const f32x2 lz = mul2(lg2_2(z), dup2(SCCODA_LN2F));
+    const f32x2 l1p = log1p_pos2(mul2(c, yinv));
+    const f32x2 common = fma2(add2(y, dup2(-0.5f)), l1p, add2(stirling_rem2(rcp2(z)), mul2(ycst, dup2(-1.0f))));
+    const f32x2 shift = fma2(c, add2(lz, dup2(-1.0f)), common);
+    const f32x2 rc = rcp2(c);
+    const f32x2 a = mul2(add2(c, dup2(-0.5f)), log1p_pos2(mul2(y, rc)));
+    const f32x2 joint = add2(add2(a, fma2(lz, dup2(0.5f), dup2(-SCCODA_HALF_LN_2PI_F))), add2(common, mul2(stirling_rem2(rc), dup2(-1.0f))));
+    return pk2(lo2(c) >= c_joint ? lo2(joint) : lo2(shift), hi2(c) >= c_joint ? hi2(joint) : hi2(shift));
+}
+
+__device__ __forceinline__ f32x2 lgamma_shift_big2(f32x2 c, f32x2 y, f32x2 ycst, f32x2 yinv) {
+    const f32x2 z = add2(c, y);
+    const f32x2 w = rcp2(z);
+    const f32x2 l1p = log1p_pos2(mul2(c, yinv));
     const f32x2 cterm = fma2(mul2(c, dup2(SCCODA_LN2F)), lg2_2(z), mul2(c, dup2(-1.0f)));     // c (ln z - 1)
     const f32x2 w2 = mul2(w, w);
     const f32x2 rem = mul2(w, fma2(w2, fma2(w2, dup2(1.0f / 1260.0f), dup2(-1.0f / 360.0f)), dup2(1.0f / 12.0f)));
@@ -463,8 +485,23 @@ static __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off,
                 acc += lgamma_shift(pc[__float_as_int(v.z)], v.x, v.y);
             }
         } else {
+            // counts >= 6 two at a time, the form chosen per element; the rest one by one
+            f32x2 acc2 = dup2(0.0f);
+            int e = lane;
 #pragma unroll 1
-            for (int e = lane; e < t.NK; e += 32) {
+            for (; e + 32 < t.nbig; e += 64) {
+                const float4 va = el[e], vb = el[e + 32];
+                acc2 = add2(acc2, lgamma_mixed_big2(pk2(pc[__float_as_int(va.z)], pc[__float_as_int(vb.z)]), pk2(va.x, vb.x),
+                                                    pk2(va.y, vb.y), pk2(va.w, vb.w), c_joint));
+            }
+            acc = lo2(acc2) + hi2(acc2);
+            if (e < t.nbig) {
+                const float4 v = el[e];
+                const float cc = pc[__float_as_int(v.z)];
+                acc += cc >= c_joint ? lgamma_joint(cc, v.x, v.y) : lgamma_shift_big(cc, v.x, v.y);
+            }
+#pragma unroll 1
+            for (e = t.nbig + lane; e < t.NK; e += 32) {
                 const float4 v = el[e];
                 const float cc = pc[__float_as_int(v.z)];
                 acc += cc >= c_joint ? lgamma_joint(cc, v.x, v.y) : lgamma_shift(cc, v.x, v.y);

@@ -442,8 +442,23 @@ static __device__ __noinline__ double mg_value(const MgTile& t, uint32_t pc_off,
                 acc += lgamma_shift(pc[__float_as_int(v.z)], v.x, v.y);
             }
         } else {
+            // counts >= 6 two at a time, the form chosen per element (lgamma_mixed_big2); the rest one by one
+            f32x2 acc2 = dup2(0.0f);
+            int e = lane;
 #pragma unroll 1
-            for (int e = lane; e < t.NK; e += 32) {
+            for (; e + 32 < t.nbig; e += 64) {
+                const float4 va = el[e], vb = el[e + 32];
+                acc2 = add2(acc2, lgamma_mixed_big2(pk2(pc[__float_as_int(va.z)], pc[__float_as_int(vb.z)]), pk2(va.x, vb.x),
+                                                    pk2(va.y, vb.y), pk2(va.w, vb.w), c_joint));
+            }
+            acc = lo2(acc2) + hi2(acc2);
+            if (e < t.nbig) {
+                const float4 v = el[e];
+                const float cc = pc[__float_as_int(v.z)];
+                acc += cc >= c_joint ? lgamma_joint(cc, v.x, v.y) : lgamma_shift_big(cc, v.x, v.y);
+            }
+#pragma unroll 1
+            for (e = t.nbig + lane; e < t.NK; e += 32) {
                 const float4 v = el[e];
                 const float cc = pc[__float_as_int(v.z)];
                 acc += cc >= c_joint ? lgamma_joint(cc, v.x, v.y) : lgamma_shift(cc, v.x, v.y);

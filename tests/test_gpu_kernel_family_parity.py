@@ -115,6 +115,35 @@ def test_four_covariates_factorial():
     _check(x, y, 3, KIND_MG, n_states=6, seed=4, scale=0.3)
 
 
+@pytest.mark.parametrize("kind", [1, KIND_CC, KIND_MG])
+def test_value_with_some_large_concentrations(kind):
+    """States in which a few cell types have concentrations of 300 ... 60,000 while the others stay small: the value pass
+    takes the joint (cancellation-free) form for the elements of those pairs only — two counts at a time with the form
+    chosen per element (lgamma_mixed_big2).  |logp - oracle| stays at the fp32 level of the ordinary states."""
+    from oracle import np_oracle as o
+    from sccoda_b200._pack import pack
+    from sccoda_b200.engine import DeviceProblem
+    from sccoda_b200.util.data_generation import generate_sweep
+    xs, ys, _ = generate_sweep(3, K=20, n_per_group=10, n_total=5000, seed0=1234)
+    ys[1, 4, 7] = 0
+    rs = np.random.RandomState(3)
+    C = 10
+    prob = DeviceProblem(pack(xs, ys, 19, dtype=np.float32), chains=C)
+    th = np.stack([random_states(rs, 1, 20, C, scale=0.4) for _ in range(3)])
+    for c in range(C):
+        big = rs.choice(20, size=1 + c % 3, replace=False)
+        th[:, c, -20 + big] = rs.uniform(5.8, 11.0, size=big.size)            # c = 330 ... 60,000
+    lp, g = prob.logp_grad(th, kernel_kind=kind)
+    lp, g = lp.cpu().numpy(), g.double().cpu().numpy()
+    for b in range(3):
+        m = o.prepare(xs[b], ys[b], 19)
+        for c in range(C):
+            ref = o.logp(th[b, c], m)
+            assert abs(lp[b, c] - ref) <= 2e-6 * abs(ref) + 5e-3, (kind, b, c, lp[b, c], ref)
+            gr = o.grad(th[b, c], m)
+            assert np.abs(g[b, c] - gr).max() <= REL * np.abs(gr).max()
+
+
 def test_wrong_shape_is_refused():
     from sccoda_b200._pack import pack
     from sccoda_b200.engine import DeviceProblem
