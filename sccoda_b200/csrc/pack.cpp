@@ -355,12 +355,19 @@ int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, con
 
     auto typed_copies = [&]() {
         if (dtype != SCCODA_F32) return;
-        auto cv = [](const std::vector<double>& s, std::vector<float>& d) {
-            d.resize(s.size());
-            for (size_t i = 0; i < s.size(); ++i) d[i] = (float)s[i];
-        };
-        cv(pk->ntot, pk->ntot32); cv(pk->xu, pk->xu32); cv(pk->ey, pk->ey32); cv(pk->eycst, pk->eycst32);
-        cv(pk->iy, pk->iy32); cv(pk->pcoef, pk->pcoef32); cv(pk->oy, pk->oy32);
+        struct Job { const std::vector<double>* s; std::vector<float>* d; };
+        Job jobs[] = {{&pk->ntot, &pk->ntot32}, {&pk->xu, &pk->xu32}, {&pk->ey, &pk->ey32}, {&pk->eycst, &pk->eycst32},
+                      {&pk->iy, &pk->iy32}, {&pk->pcoef, &pk->pcoef32}, {&pk->oy, &pk->oy32}};
+        for (auto& j : jobs) j.d->resize(j.s->size());
+        const int chunks = threads * 4;                       // every array in `chunks` slices, converted in parallel
+        parallel_for(chunks, threads, [&](int ch) {
+            for (auto& j : jobs) {
+                const size_t n = j.s->size(), lo = n * ch / chunks, hi = n * (ch + 1) / chunks;
+                const double* s = j.s->data();
+                float* d = j.d->data();
+                for (size_t i = lo; i < hi; ++i) d[i] = (float)s[i];
+            }
+        });
     };
     auto set_nbig_min = [&]() {
         int m = pk->nbig[0];
@@ -368,13 +375,34 @@ int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, con
         pk->nbig_min = m;
     };
 
+    if (grouped && grouped_req < 0) {
+        // The automatic choice asks the library's own launch planner (NUTS with the default tree depth = the largest
+        // footprint) whether the pair/item arrays of a dataset fit one CTA's shared memory; very long datasets take the
+        // element layout.  The plan depends on the sizes only (and on nbig_min of the grouped list order = the smallest
+        // number of counts >= 6 of a dataset), not on the order of the element list: asked before anything is reordered.
+        int nb_min = (int)NK;
+        for (int b = 0; b < B; ++b) {
+            const double* ey = pk->ey.data() + (size_t)b * NK;
+            int nb = 0;
+            for (size_t e = 0; e < NK; ++e) nb += ey[e] >= 6.0;
+            nb_min = std::min(nb_min, nb);
+        }
+        sccoda_problem prob;
+        pk->grouped = 1;
+        pk->nbig_min = nb_min;
+        sccoda_packed_problem(pk, 1, &prob);
+        const int dummy = 0;                                  // the planner only checks that the arrays are there
+        const void* any = &dummy;
+        prob.ey = prob.eycst = prob.ntot = prob.xu = prob.iy = prob.pcoef = prob.oy = any;
+        sccoda_sampler smp;
+        std::memset(&smp, 0, sizeof(smp));
+        smp.method = SCCODA_METHOD_NUTS; smp.num_results = 1; smp.num_leapfrog = 10; smp.max_tree_depth = 10;
+        smp.step_size = 0.01; smp.target_accept = 0.75; smp.store_draws = 1;
+        int32_t w, c, g, sm;
+        if (sccoda_launch_plan(&prob, &smp, &w, &c, &g, &sm) == -9) grouped = 0;
+    }
     if (grouped) {
         // only the value pass walks the element list of the grouped layout: every count >= 6 first (stable partition)
-        std::vector<double> ey0, ec0;
-        std::vector<uint32_t> ei0;
-        std::vector<int32_t> nbig0;
-        const bool may_revert = grouped_req < 0;
-        if (may_revert) { ey0 = pk->ey; ec0 = pk->eycst; ei0 = pk->eidx; nbig0 = pk->nbig; }
         parallel_for(B, threads, [&](int b) {
             double* ey = pk->ey.data() + (size_t)b * NK;
             double* ec = pk->eycst.data() + (size_t)b * NK;
@@ -392,23 +420,6 @@ int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, con
         pk->grouped = 1;
         set_nbig_min();
         typed_copies();
-        if (may_revert) {
-            // ask the library's own launch planner (NUTS with the default tree depth = the largest footprint) whether the
-            // pair/item arrays of a dataset fit one CTA's shared memory; very long datasets take the element layout
-            sccoda_problem prob;
-            sccoda_packed_problem(pk, 1, &prob);
-            sccoda_sampler smp;
-            std::memset(&smp, 0, sizeof(smp));
-            smp.method = SCCODA_METHOD_NUTS; smp.num_results = 1; smp.num_leapfrog = 10; smp.max_tree_depth = 10;
-            smp.step_size = 0.01; smp.target_accept = 0.75; smp.store_draws = 1;
-            int32_t w, c, g, sm;
-            if (sccoda_launch_plan(&prob, &smp, &w, &c, &g, &sm) == -9) {
-                pk->ey = ey0; pk->eycst = ec0; pk->eidx = ei0; pk->nbig = nbig0;
-                pk->grouped = 0;
-                set_nbig_min();
-                typed_copies();
-            }
-        }
     } else {
         pk->grouped = 0;
         set_nbig_min();
