@@ -62,6 +62,13 @@ double np_pairwise(const double* a, long n) {
 }
 double np_sum(const double* a, long n) { return np_pairwise(a, n); }
 
+// lgamma without the write to the global `signgam` (every thread of the packer calls it ~800 times per dataset: the
+// shared cache line would bounce between the cores)
+inline double lgamma_mt(double v) {
+    int sign;
+    return ::lgamma_r(v, &sign);
+}
+
 template <typename F>
 void parallel_for(int n, int threads, F&& f) {
     if (threads <= 1 || n <= 1) {
@@ -199,14 +206,14 @@ int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, con
                 for (int d = 0; d < D; ++d) pk->xu[((size_t)b * Umax + s.grp[n]) * D + d] = xb[(size_t)s.order[n] * D + d];
         // constants (fp64): multinomial coefficient, priors and — fp32 build — sum lgamma(y), see special.cuh
         double lc = 0.0, lgsum = 0.0;
-        for (int n = 0; n < N; ++n) lc += std::lgamma(nt[n] + 1.0);
+        for (int n = 0; n < N; ++n) lc += lgamma_mt(nt[n] + 1.0);
         std::vector<double> ycst(NK, 0.0);
         double ly1 = 0.0;
         for (size_t e = 0; e < NK; ++e) {
             const double v = yb[e];
-            ly1 += std::lgamma(v + 1.0);
+            ly1 += lgamma_mt(v + 1.0);
             if (dtype == SCCODA_F32) {
-                const double lg = std::lgamma(v);
+                const double lg = lgamma_mt(v);
                 lgsum += lg;
                 ycst[e] = v >= 6.0 ? lg - ((v - 0.5) * std::log(v) - v + 0.5 * LOG_2PI) : lg;   // r(y) / lgamma(y)
             }
