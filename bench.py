@@ -400,14 +400,16 @@ def run_ours(a):
     traffic = traffic_from_profile(out.kernel_kind, a, world)
     plan = prob.plan(sh.smp)
     wide = out.kernel_kind == 3 and plan[1] > C                 # one CTA per SM with a share of all chains (hmc_cc.cuh)
-    lat = out.kernel_kind == 3 and not wide and plan[2] * plan[1] * plan[0] <= 148 * 16
+    n_warps = plan[2] * plan[1] * plan[0]
+    cc_name = ("hmc_cc_wide_kernel" if wide else "hmc_cc_lat_kernel" if n_warps <= 148 * 12 else
+               "hmc_cc_lat16_kernel" if n_warps <= 148 * 16 else "hmc_cc_kernel")       # kernels_cc.cu: launch_hmc_cc
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None,
                 "traffic": traffic["bytes"] if traffic else None, "traffic_detail": traffic,
                 "peak_source": "FFMA micro-kernel measured in this run on this device (sccoda_measure_peaks); "
                                "MEASURED_PEAKS.json has no fp32 entry",
                 "mufu_peak_tops": mufu_peak,
-                "kernel": {1: "hmc_kernel<float,W,grouped>", 3: "hmc_cc_wide_kernel" if wide else ("hmc_cc_lat_kernel" if lat else "hmc_cc_kernel"),
+                "kernel": {1: "hmc_kernel<float,W,grouped>", 3: cc_name,
                            5: "hmc_mg_kernel<D>"}.get(out.kernel_kind, "hmc_kernel"), "kernel_ms": k_ms,
                 "summary_kernel_ms": s_ms, "algorithmic_flop_per_launch": flops_launch,
                 "flop_model": "per grad-eval 64NK+48N+4NKD, per value 28(2NK+2N) (SURVEY 8d)",

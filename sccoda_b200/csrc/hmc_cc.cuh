@@ -523,9 +523,10 @@ static __device__ __noinline__ double cc_value(const CcTile& t, uint32_t pc_off,
 // The body is shared by two entry points that differ in their register budget only:
 //   hmc_cc_kernel      72 registers, 7 CTAs of 128 threads per SM: every chain of a full sweep (>= ~2400 chains) resident
 //   hmc_cc_wide_kernel the same budget as ONE CTA of up to 28 warps per SM (see WIDE below): the sweep's launch
-//   hmc_cc_lat_kernel  no register cap: for launches that leave the device under-filled (a shard of the sweep on each
-//                      of 8 GPUs: 512 chains on 592 schedulers), where one warp per scheduler runs at the latency of its
-//                      own dependency chains and the spills / re-materialisations of the capped build are pure loss
+//   hmc_cc_lat_kernel, hmc_cc_lat16_kernel  no register cap / 128 instead of 72 registers: for launches that leave the
+//                      device under-filled (at most 12 / 16 warps per SM, e.g. a shard of the sweep on each of 8 GPUs:
+//                      512 chains on 592 schedulers), where a warp runs at the latency of its own dependency chains and
+//                      the spills / re-materialisations of the capped build are pure loss
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -772,6 +773,8 @@ __global__ void __launch_bounds__(128) logp_grad_cc_kernel(const __grid_constant
     }
     if (lane == 0) a.carry[chain] = lp;
 }
+// (128, 4): at most 128 registers, so that 16 warps per SM are resident at once; (128, 1): no cap, up to 12 warps per SM
+__global__ void __launch_bounds__(128, 4) hmc_cc_lat16_kernel(const __grid_constant__ KArgs a) { hmc_cc_body<false>(a); }
 __global__ void __launch_bounds__(128, 1) hmc_cc_lat_kernel(const __grid_constant__ KArgs a) { hmc_cc_body<false>(a); }
 
 // ------------------------------------------------------------------------------------------------

@@ -3,9 +3,11 @@
 
 namespace sccoda {
 cudaError_t launch_hmc_cc(const KArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
-    // under-filled device (at most 16 warps per SM could ever be resident): the uncapped build (hmc_cc.cuh)
-    const bool lat = (long long)grid * (block / 32) <= 148LL * 16;
-    auto* fn = a.wide > 0 ? hmc_cc_wide_kernel : (lat ? hmc_cc_lat_kernel : hmc_cc_kernel);
+    // under-filled device: the builds with a larger register budget (hmc_cc.cuh), as long as every CTA of the launch is
+    // still resident at once (3 CTAs of 128 threads per SM without a cap, 4 with 128 registers)
+    const long long warps = (long long)grid * (block / 32);
+    auto* fn = a.wide > 0 ? hmc_cc_wide_kernel
+                          : (warps <= 148LL * 12 ? hmc_cc_lat_kernel : (warps <= 148LL * 16 ? hmc_cc_lat16_kernel : hmc_cc_kernel));
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     fn<<<grid, block, smem, st>>>(a);
