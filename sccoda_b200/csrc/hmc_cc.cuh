@@ -153,6 +153,14 @@ __device__ __forceinline__ float warp_sum1(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Two dot products of the U-turn criterion at once, in fp32: only their signs are used, and the six shuffles of
+// warp_sum2 (+ one exchange) replace twenty 32-bit shuffles and ten fp64 additions of two double-precision sums.
+__device__ __forceinline__ void warp_dots2(float a, float b, int lane, float& sa, float& sb) {
+    const float v = warp_sum2(a, b, lane);                        // lanes 0..15: sum(a), lanes 16..31: sum(b)
+    const float o = __shfl_xor_sync(0xffffffffu, v, 16);
+    sa = lane < 16 ? v : o;
+    sb = lane < 16 ? o : v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Staging: the packed dataset (include/sccoda_b200.h) re-laid lane-major into shared memory (CcPlan, kernels.h)
@@ -933,11 +941,12 @@ __global__ void __launch_bounds__(128, 4) nuts_cc_kernel(const __grid_constant__
                     for (int sidx = idx_max; sidx > idx_max - n_chk && no_uturn; --sidx) {
                         const CcVec cp = cc_ld(slots + 32 * (S_CKP + sidx)), cr = cc_ld(slots + 32 * (S_CKR + sidx));
                         const CcVec span = {rho_s.a - cr.a + cp.a, rho_s.b - cr.b + cp.b, rho_s.i - cr.i + cp.i, rho_s.s - cr.s + cp.s};
-                        const double D1 = warp_sum_d((double)cc_dot(span, cp, lane)), D2 = warp_sum_d((double)cc_dot(span, p, lane));
+                        float D1, D2;
+                        warp_dots2(cc_dot(span, cp, lane), cc_dot(span, p, lane), lane, D1, D2);
                         if (!(D1 >= 0.0 && D2 >= 0.0)) no_uturn = false;
                     }
                 }
-                double energy = lqv - 0.5 * warp_sum_d((double)kk);
+                double energy = lqv - 0.5 * (double)warp_sum1(kk);   // kinetic energy ~ P / 2: fp32 sum, error ~1e-6
                 if (isnan(energy)) energy = -CUDART_INF;
                 const double delta = energy - e0;
                 const bool divergent = !(-delta < 1000.0);
@@ -976,8 +985,8 @@ __global__ void __launch_bounds__(128, 4) nuts_cc_kernel(const __grid_constant__
             CcVec rho = cc_ld(slots + 32 * S_RHO);
             rho.a += rho_s.a; rho.b += rho_s.b; rho.i += rho_s.i; rho.s += rho_s.s;
             cc_st(slots + 32 * S_RHO, rho);
-            const double D1 = warp_sum_d((double)cc_dot(rho, cc_ld(slots + 32 * S_LP), lane));
-            const double D2 = warp_sum_d((double)cc_dot(rho, cc_ld(slots + 32 * S_RP), lane));
+            float D1, D2;
+            warp_dots2(cc_dot(rho, cc_ld(slots + 32 * S_LP), lane), cc_dot(rho, cc_ld(slots + 32 * S_RP), lane), lane, D1, D2);
             if (forward) r_lp = lqv; else l_lp = lqv;
             cont = alive && (D1 >= 0.0) && (D2 >= 0.0);
             depth += 1;

@@ -915,11 +915,12 @@ __global__ void __launch_bounds__(128, mg_nuts_ctas(D, NS)) nuts_mg_kernel(const
                         V span = rho_s;
                         mg_axpy<D, NS>(span, T(-1), mg_ld<D, NS>(slot(S_CKR + sidx)));
                         mg_axpy<D, NS>(span, T(1), cp);
-                        const double D1 = mg_sum_d((double)mg_dot<D, NS>(span, cp, lane)), D2 = mg_sum_d((double)mg_dot<D, NS>(span, p, lane));
+                        float D1, D2;
+                        warp_dots2(mg_dot<D, NS>(span, cp, lane), mg_dot<D, NS>(span, p, lane), lane, D1, D2);
                         if (!(D1 >= 0.0 && D2 >= 0.0)) no_uturn = false;
                     }
                 }
-                double energy = lqv - 0.5 * mg_sum_d((double)kk);
+                double energy = lqv - 0.5 * (double)warp_sum1(kk);   // kinetic energy ~ P / 2: fp32 sum, error ~1e-6
                 if (isnan(energy)) energy = -CUDART_INF;
                 const double delta = energy - e0;
                 const bool divergent = !(-delta < 1000.0);
@@ -958,8 +959,8 @@ __global__ void __launch_bounds__(128, mg_nuts_ctas(D, NS)) nuts_mg_kernel(const
             V rho = mg_ld<D, NS>(slot(S_RHO));
             mg_axpy<D, NS>(rho, T(1), rho_s);
             mg_st<D, NS>(slot(S_RHO), rho);
-            const double D1 = mg_sum_d((double)mg_dot<D, NS>(rho, mg_ld<D, NS>(slot(S_LP)), lane));
-            const double D2 = mg_sum_d((double)mg_dot<D, NS>(rho, mg_ld<D, NS>(slot(S_RP)), lane));
+            float D1, D2;
+            warp_dots2(mg_dot<D, NS>(rho, mg_ld<D, NS>(slot(S_LP)), lane), mg_dot<D, NS>(rho, mg_ld<D, NS>(slot(S_RP)), lane), lane, D1, D2);
             if (forward) r_lp = lqv; else l_lp = lqv;
             cont = alive && (D1 >= 0.0) && (D2 >= 0.0);
             depth += 1;
