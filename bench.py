@@ -401,7 +401,8 @@ def run_ours(a):
     plan = prob.plan(sh.smp)
     wide = out.kernel_kind == 3 and plan[1] > C                 # one CTA per SM with a share of all chains (hmc_cc.cuh)
     n_warps = plan[2] * plan[1] * plan[0]
-    cc_name = ("hmc_cc_wide_kernel" if wide else "hmc_cc_lat_kernel" if n_warps <= 148 * 12 else
+    cc_name = (("hmc_cc_wide_kernel" if plan[1] > 16 else "hmc_cc_wide16_kernel") if wide else
+               "hmc_cc_lat_kernel" if n_warps <= 148 * 12 else
                "hmc_cc_lat16_kernel" if n_warps <= 148 * 16 else "hmc_cc_kernel")       # kernels_cc.cu: launch_hmc_cc
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None,

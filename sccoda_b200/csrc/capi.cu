@@ -172,15 +172,17 @@ int make_plan(const sccoda_problem* p, sccoda::KArgs& a, int& kind, int W_req, i
         }
         out->W = W; out->cpc = cpc; out->smem = (int)smem;
         out->grid = p->B * ((p->C + cpc - 1) / cpc);
-        // A launch with more than 16 chains per SM on the case/control HMC kernel (beyond the reach of the uncapped
-        // build, kernels_cc.cu): one wide CTA per SM holding a balanced share of the chains, its warps meeting at a
-        // barrier every 16 transitions (hmc_cc.cuh: WIDE)
+        // A launch with more than 8 chains per SM on the case/control HMC kernel: one wide CTA per SM holding a balanced
+        // share of the chains, its warps meeting at a barrier every 16 transitions (hmc_cc.cuh: WIDE; up to 16 chains
+        // per SM with a 128-register build, beyond that the 72-register build that keeps 28 warps resident)
         a.wide = 0;
         const long long n_chains = (long long)p->B * p->C;
         // warps one SM holds of this kernel (its register budget): 28 for the case/control kernel, 4 x the resident CTAs
         // of 128 threads the multi-group kernel is compiled for
         const int wmax = kind == sccoda::KIND_HMC_CC ? 28 : (kind == sccoda::KIND_HMC_MG ? 4 * sccoda::mg_hmc_ctas(p->D, p->K <= 31 ? 1 : 2) : 0);
-        const long long wide_from = kind == sccoda::KIND_HMC_CC ? 16 : (wmax * 2) / 3;   // chains per SM from which the wide launch pays
+        // chains per SM from which the wide launch pays (measured: 10 and 12 chains per SM +3 %, 14 ... 16 +9 %, 21 ... 28
+        // +15 ... 18 %; 7 and 8 chains per SM -2 %)
+        const long long wide_from = kind == sccoda::KIND_HMC_CC ? 8 : (wmax * 2) / 3;
         // ... and only when the CTAs of the launch fill whole waves: one wave, or several with the last one >= 90 % full
         // (a CTA holds the SM alone; a sparse last wave costs more than the fair scheduling gains)
         const long long per_wave = (long long)n_sm * (wmax > 0 ? wmax : 1);

@@ -730,6 +730,8 @@ __device__ __forceinline__ void hmc_cc_body(const KArgs& a) {
 
 __global__ void __launch_bounds__(128, 7) hmc_cc_kernel(const __grid_constant__ KArgs a) { hmc_cc_body<false>(a); }
 __global__ void __launch_bounds__(896, 1) hmc_cc_wide_kernel(const __grid_constant__ KArgs a) { hmc_cc_body<true>(a); }
+// the wide geometry for 13 ... 16 chains per SM: half the warps, 128 registers
+__global__ void __launch_bounds__(512, 1) hmc_cc_wide16_kernel(const __grid_constant__ KArgs a) { hmc_cc_body<true>(a); }
 
 // K1cc — value and gradient at given states through cc_grad / cc_value, i.e. exactly what the sampler above evaluates
 // at every leapfrog (sccoda_logp_grad_as; target_log_prob_fn + autodiff of scCODA_model.py:756-760): theta[B,C,P] in

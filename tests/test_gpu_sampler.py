@@ -664,9 +664,9 @@ def test_host_buffer_entry_point_matches_device_path():
     assert np.array_equal(summ, summ_dev)
 
 
-@pytest.mark.parametrize("B,C", [(640, 4), (900, 3), (2500, 1), (828, 5), (2072, 4)])   # the last one: two full waves
+@pytest.mark.parametrize("B,C", [(640, 4), (900, 3), (2500, 1), (828, 5), (2072, 4), (400, 4)])   # two full waves; 11 chains per SM
 def test_wide_launch_is_bit_identical_to_one_dataset_per_cta(B, C):
-    """Launches with more than 16 chains per SM take the wide geometry of the case/control HMC kernel (one CTA per SM
+    """Launches with more than 8 chains per SM take the wide geometry of the case/control HMC kernel (one CTA per SM
     with a balanced share of the chains, staging every dataset they belong to, barrier every 16 transitions); chains do
     not depend on the launch geometry: draws, statistics and the resume state are those of the classic launch."""
     from sccoda_b200._pack import pack
@@ -684,7 +684,7 @@ def test_wide_launch_is_bit_identical_to_one_dataset_per_cta(B, C):
     init[..., -20:] = rs.randn(B, C, 20)
     smp_w = prob.make_sampler(1, 40, 20, seed=5)
     smp_c = prob.make_sampler(1, 40, 20, seed=5, chains_per_cta=min(C, 4))
-    assert prob.plan(smp_w)[1] > 12 and prob.plan(smp_c)[1] == min(C, 4)
+    assert prob.plan(smp_w)[1] > 8 and prob.plan(smp_c)[1] == min(C, 4)
     ow, oc = prob.sample(init, smp_w), prob.sample(init, smp_c)
     assert ow.kernel_kind == 3 and oc.kernel_kind == 3
     assert torch_equal(ow.draws, oc.draws) and torch_equal(ow.stats, oc.stats)

@@ -71,6 +71,9 @@ def test_launch_plan_sweep_config():
     pk = pack(np.broadcast_to(x, (128,) + x.shape), np.broadcast_to(y, (128,) + y.shape), 19)
     rc, w, cpc, grid, smem = _plan(_problem(pk, 4), _sampler())
     assert rc == 0 and w == 1 and cpc == 4 and grid == 128 and 0 < smem < 48 * 1024
+    pk = pack(np.broadcast_to(x, (512,) + x.shape), np.broadcast_to(y, (512,) + y.shape), 19)      # two GPUs: 14 chains per SM
+    rc, w, cpc, grid, smem = _plan(_problem(pk, 4), _sampler())
+    assert rc == 0 and w == 1 and cpc == 14 and grid == 148
 
 
 def test_launch_plan_scales_warps_for_few_chains_and_big_models():
