@@ -210,7 +210,7 @@ int sccoda_predict(const sccoda_problem* prob, const int32_t* row_order, int32_t
                    int32_t draw_end, const void* draws, void* concentration, void* prediction, void* stream);
 
 /* Launch geometry the sampler would use (for planning / tests): warps per chain, chains per CTA, CTAs, bytes of dynamic
- * shared memory per CTA.  One warp per chain on the lane-per-cell-type kernels; HMC launches with more than ~16 chains
+ * shared memory per CTA.  One warp per chain on the lane-per-cell-type kernels; HMC launches with more than ~8 chains
  * per SM that fill whole waves take the wide geometry — one CTA per SM holding a balanced share of ALL chains (up to 28
  * for the case/control kernel) and every dataset they belong to, its warps meeting at a barrier every 16 transitions;
  * an explicit sccoda_sampler::chains_per_cta keeps one dataset per CTA.  Chains do not depend on the geometry. */
