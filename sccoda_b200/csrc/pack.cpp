@@ -6,10 +6,12 @@
 // parameter-independent constant of the log-density.  sccoda_b200/_pack.py: pack_numpy is the same layout in numpy
 // (tests/test_pack_native.py compares the two); this one is what the product calls, threaded over datasets.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <numeric>
 #include <thread>
@@ -69,6 +71,8 @@ inline double lgamma_mt(double v) {
     return ::lgamma_r(v, &sign);
 }
 
+// An exception inside a worker (std::bad_alloc) must not escape its thread: it is recorded and rethrown by the caller's
+// thread after the join (sccoda_pack turns it into an error code).
 template <typename F>
 void parallel_for(int n, int threads, F&& f) {
     if (threads <= 1 || n <= 1) {
@@ -78,12 +82,18 @@ void parallel_for(int n, int threads, F&& f) {
     if (threads > n) threads = n;
     std::vector<std::thread> pool;
     pool.reserve(threads);
+    std::atomic<bool> failed{false};
     for (int t = 0; t < threads; ++t)
         pool.emplace_back([&, t]() {
-            const int lo = (int)((long long)n * t / threads), hi = (int)((long long)n * (t + 1) / threads);
-            for (int i = lo; i < hi; ++i) f(i);
+            try {
+                const int lo = (int)((long long)n * t / threads), hi = (int)((long long)n * (t + 1) / threads);
+                for (int i = lo; i < hi && !failed.load(std::memory_order_relaxed); ++i) f(i);
+            } catch (...) {
+                failed.store(true);
+            }
         });
     for (auto& th : pool) th.join();
+    if (failed.load()) throw std::bad_alloc();
 }
 
 // items and odd counts of one dataset before the batch-wide padding (build_items of _pack.py)
@@ -107,8 +117,21 @@ extern "C" {
 
 void sccoda_packed_free(sccoda_packed* pk) { delete pk; }
 
+static int pack_impl(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, const double* y, const int32_t* ref,
+                     int32_t dtype, int32_t pseudocount, int32_t grouped_req, int32_t threads, sccoda_packed** out);
+
 int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, const double* y, const int32_t* ref,
                 int32_t dtype, int32_t pseudocount, int32_t grouped_req, int32_t threads, sccoda_packed** out) {
+    try {
+        return pack_impl(B, N, K, D, x, y, ref, dtype, pseudocount, grouped_req, threads, out);
+    } catch (const std::exception& e) {
+        if (out) *out = nullptr;
+        return sccoda_capi::set_error(-54, "sccoda_pack: %s", e.what());
+    }
+}
+
+static int pack_impl(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, const double* y, const int32_t* ref,
+                     int32_t dtype, int32_t pseudocount, int32_t grouped_req, int32_t threads, sccoda_packed** out) {
     using sccoda_capi::set_error;
     if (!out) return set_error(-50, "sccoda_pack: out is NULL");
     *out = nullptr;
@@ -123,8 +146,8 @@ int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, con
         if (threads < 1) threads = 1;
         if (threads > 32) threads = 32;
     }
-    sccoda_packed* pk = new (std::nothrow) sccoda_packed();
-    if (!pk) return set_error(-54, "sccoda_pack: out of memory");
+    std::unique_ptr<sccoda_packed> holder(new sccoda_packed());   // freed on every early return and on exceptions
+    sccoda_packed* pk = holder.get();
     pk->B = B; pk->N = N; pk->K = K; pk->D = D; pk->dtype = dtype;
     const size_t NK = (size_t)N * K;
     std::vector<DsScratch> ds(B);
@@ -178,7 +201,6 @@ int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, con
     for (int b = 0; b < B; ++b) Umax = std::max(Umax, ds[b].U);
     pk->Umax = Umax;
     if ((long long)Umax * K > 65535) {
-        delete pk;
         return set_error(-53, "packed element index needs Umax*K <= 65535 and N <= 65535");
     }
     const int NP = Umax * (K + 1);
@@ -304,7 +326,6 @@ int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, con
     int NImax = std::max(2, ni_max + (ni_max & 1)), NOmax = std::max(1, no_max), NGmax = std::max(1, ng_max);
     bool items_ok = !((long long)NP * NF > 65535 || NImax > 65535 || NOmax > 65535);
     if (!items_ok && grouped_req > 0) {
-        delete pk;
         return set_error(-55, "pair/item layout needs Umax*(K+1)*NF <= 65535 and at most 65535 items / odd counts");
     }
     pk->NI.assign(B, 0);
@@ -432,7 +453,7 @@ int sccoda_pack(int32_t B, int32_t N, int32_t K, int32_t D, const double* x, con
         set_nbig_min();
         typed_copies();
     }
-    *out = pk;
+    *out = holder.release();
     return 0;
 }
 
