@@ -75,6 +75,21 @@ def test_pseudocounts_small_and_non_integer_counts(kind):
     _check(x, y, 5, kind, seed=2)
 
 
+@pytest.mark.parametrize("kind", [KIND_CC, KIND_MG])
+def test_many_odd_counts_per_pair(kind):
+    """The odd counts of a pair ride in its item slots as y + 6 (cc_stage / mg_stage): pairs whose padding does not hold
+    them all (7 zeros beside 3 large counts: a second item appears), several DISTINCT odd values in one pair (0.25, 0.5,
+    2.5, 5.75 -> one rational correction each), a pair with odd counts only, and a column of zeros."""
+    x, y = synthetic_dataset(21, N=20, K=9, D=1)
+    y[:7, 0] = 0                                   # group 0: 7 pseudocounts + 3 large counts
+    y[10:, 1] = [0, 0.25, 2.5, 5.75, 0, 0.25, 3, 1, 0, 7]          # group 1: mixed odd / small / large
+    y[:10, 2] = 0.5                                # group 0: odd counts only (the data already hold 0.5)
+    y[:, 3] = 0                                    # a cell type that was never seen
+    y[3, 4] = 1e-3                                 # a tiny non-integer count
+    _check(x, y, 8, kind, seed=5)
+    _check(x, y, 0, kind, n_states=6, seed=6)      # ... with the sparse column as the reference
+
+
 @pytest.mark.parametrize("K", [2, 3, 17, 31])
 @pytest.mark.parametrize("kind", [KIND_CC, KIND_MG])
 def test_cell_type_counts_one_per_lane(kind, K):
