@@ -229,6 +229,7 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
         const int p = ipair[it], tt = ipos[it] - p * a.NF;
         int u, col;
         cc_pair_to_col(p, K, u, col);
+        if (tt < 0 || tt >= a.NT || col > K || u > 1) continue;   // a layout that contradicts its own header: never write outside the tile
         yv[((tt * kItemR + j) * 32 + col) * 2 + u] = iy[j * a.NImax + it];
         if (j == 0) {
             atomicMax(&bounds[0], tt + 1);
@@ -247,11 +248,15 @@ __device__ __forceinline__ void cc_stage(const KArgs& a, int b, const CcPlan& pl
         const uint32_t od = a.odesc[(size_t)b * a.NGmax + q];
         int u, col;
         cc_pair_to_col(a.opair[(size_t)b * a.NGmax + q], K, u, col);
-        const int base = fill[col * 2 + u], n = (int)(od >> 16);
+        if (col > K || u > 1) continue;
+        const int base = fill[col * 2 + u];
+        int n = (int)(od >> 16);
+        if (n > a.NOT) n = a.NOT;                                // (the header's bounds are what the tile was sized for)
         int nd = 0;
         for (int tt = 0; tt < n; ++tt) {
             const float y = oy[(od & 0xffffu) + tt];
             const int slot = base + tt;
+            if (slot >= pl.NTC * kItemR) break;
             yv[(slot * 32 + col) * 2 + u] = y + 6.0f;            // slot = item * R + position
             int d = 0;
             while (d < nd && ov[(d * 32 + col) * 2 + u] != y) ++d;

@@ -48,7 +48,7 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
 __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl, int UPmax, int NS, MgTile& t) {
     using T = float;
     const int N = a.dm.N, K = a.dm.K, D = a.dm.D, NK = a.dm.NK, Umax = a.Umax, NP = Umax * (K + 1);
-    const int NOT = a.NOT;
+    const int NT = a.NT, NOT = a.NOT;
     t.cf = pin_u32((uint32_t)pl.cf); t.yv = pin_u32((uint32_t)pl.yv); t.ov = pin_u32((uint32_t)pl.ov);
     t.om = pin_u32((uint32_t)pl.om);
     t.rows = pin_u32((uint32_t)pl.rows); t.el = pin_u32((uint32_t)pl.el); t.xg = pin_u32((uint32_t)pl.xg);
@@ -110,6 +110,7 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
         int u, col;
         mg_pair_to_col(p, K, Umax, u, col);
         const int q = (u >> 1) * NS + (col >> 5);
+        if (tt < 0 || tt >= NT || col > K || u >= 2 * UPmax) continue;   // never write outside the tile
         yv[(((q * NTC + tt) * kItemR + j) * 32 + (col & 31)) * 2 + (u & 1)] = iy[j * a.NImax + it];
         if (j == 0) {
             atomicMax(&bounds[q], tt + 1);
@@ -125,12 +126,16 @@ __device__ __forceinline__ void mg_stage(const KArgs& a, int b, const MgPlan& pl
         const uint32_t od = a.odesc[(size_t)b * a.NGmax + q];
         int u, col;
         mg_pair_to_col(a.opair[(size_t)b * a.NGmax + q], K, Umax, u, col);
+        if (col > K || u >= 2 * UPmax) continue;
         const int qq = (u >> 1) * NS + (col >> 5), cl = col & 31, h = u & 1;
-        const int base = fill[(qq * 32 + cl) * 2 + h], n = (int)(od >> 16);
+        const int base = fill[(qq * 32 + cl) * 2 + h];
+        int n = (int)(od >> 16);
+        if (n > NOT) n = NOT;
         int nd = 0;
         for (int tt = 0; tt < n; ++tt) {
             const float y = oy[(od & 0xffffu) + tt];
             const int slot = base + tt;                          // item * R + position
+            if (slot >= NTC * kItemR) break;
             yv[((qq * NTC * kItemR + slot) * 32 + cl) * 2 + h] = y + 6.0f;
             int d = 0;
             while (d < nd && ov[((qq * NOT + d) * 32 + cl) * 2 + h] != y) ++d;
