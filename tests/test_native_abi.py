@@ -214,3 +214,30 @@ def test_problem_struct_matches_header():
 def test_check_raises_runtime_error():
     with pytest.raises(RuntimeError, match="failed"):
         nat.check(-3, "unit-test")
+
+
+def test_product_never_touches_the_oracle_and_fails_loudly_without_the_library(tmp_path, monkeypatch):
+    """The oracle is test infrastructure: nothing under sccoda_b200/ may import, load or execute anything under oracle/
+    (only tests/, __graft_entry__.smoke() and bench.py's CPU legs do), and without the native library every entry point
+    raises instead of falling back."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|libdm_oracle|oracle[/\\]", re.M)
+    for dirpath, _, files in os.walk(os.path.join(root, "sccoda_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".sh")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8", errors="replace").read()
+                assert not pat.search(text), os.path.join(dirpath, f)
+    code = ("import numpy as np\n"
+            "from sccoda_b200._pack import pack\n"
+            "try:\n"
+            "    pack(np.zeros((4, 1)), np.ones((4, 3)), 0)\n"
+            "except RuntimeError as e:\n"
+            "    assert 'no CPU fallback' in str(e).replace('There is no', 'no'), e\n"
+            "    print('raised')\n")
+    env = dict(os.environ, SCCODA_B200_LIB=str(tmp_path / "missing.so"), PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and "raised" in out.stdout, out.stderr[-500:]
